@@ -1,0 +1,92 @@
+"""Import the UNMODIFIED reference modules from /root/reference (build container
+only -- the GPU box has no /root/reference, so nothing that runs there may import
+this file).  TEST INFRASTRUCTURE: used by ``oracle/make_golden.py`` and by the
+CPU tests that pin the oracle against the live reference when it is present.
+
+``ldm.models.autoencoder`` imports ``pytorch_lightning`` and ``taming`` at module
+import time (autoencoder.py:2,6); neither is installed and neither is touched by
+``AutoencoderKL.encode``, so tiny stand-ins are registered in ``sys.modules``.
+No reference source is copied or modified.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = "/root/reference"
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "src", "stable-diffusion", "ldm"))
+
+
+def _install_import_stubs():
+    import torch.nn as nn
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+        pl.LightningModule = nn.Module
+        sys.modules["pytorch_lightning"] = pl
+    if "taming" not in sys.modules:
+        names = ["taming", "taming.modules", "taming.modules.vqvae", "taming.modules.vqvae.quantize"]
+        mods = [types.ModuleType(n) for n in names]
+        for n, m in zip(names, mods):
+            sys.modules[n] = m
+        mods[-1].VectorQuantizer2 = type("VectorQuantizer2", (nn.Module,), {})
+
+
+def autoencoder_kl(sd=None):
+    """The reference ``AutoencoderKL`` with the kl-f8 ddconfig, eval mode."""
+    _install_import_stubs()
+    p = os.path.join(REF_ROOT, "src", "stable-diffusion")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    from ldm.models.autoencoder import AutoencoderKL  # noqa: E402
+    from . import kl_f8
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = AutoencoderKL(ddconfig=dict(kl_f8.DDCONFIG), lossconfig={"target": "torch.nn.Identity"},
+                          embed_dim=4)
+    if sd is not None:
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing), missing
+    return m.eval()
+
+
+def _load_file(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def percep_module():
+    return _load_file("ref_percep_RBVAE_model",
+                      os.path.join(REF_ROOT, "models/percep_RBVAE/percep_RBVAE_model.py"))
+
+
+def contrastive_module():
+    return _load_file("ref_contrastive_RBVAE_model",
+                      os.path.join(REF_ROOT, "models/contrastive_RBVAE/contrastive_RBVAE_model.py"))
+
+
+def rbvae(kind, in_channels, latent_dim, sd=None, feat_hw=None):
+    """Reference ``Seq2SeqBinaryVAE``; if ``feat_hw`` differs from the hard-wired
+    fc size the fc *module attribute* is replaced on the instance
+    (the reference file is untouched) so square BASELINE shapes can run."""
+    import torch.nn as nn
+    mod = percep_module() if kind == "percep" else contrastive_module()
+    m = mod.Seq2SeqBinaryVAE(in_channels=in_channels, out_channels=in_channels,
+                             latent_dim=latent_dim, hidden_dim=latent_dim)
+    if feat_hw is not None:
+        ch = m.encoder_cnn.conv[0].out_channels
+        fin = ch * feat_hw[0] * feat_hw[1]
+        if m.encoder_cnn.fc.in_features != fin:
+            m.encoder_cnn.fc = nn.Linear(fin, latent_dim)
+    if sd is not None:
+        own = m.state_dict()
+        own.update({k: v for k, v in sd.items()})
+        m.load_state_dict(own)
+    return m.eval()

@@ -1,0 +1,252 @@
+// api.cu -- the extern "C" boundary declared in include/sfv.h.
+#include "common.cuh"
+#include "encoder.h"
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+
+namespace sfv {
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int rbvae_build(SfvRbvae* r, const SfvTensor* t, int n);
+size_t rbvae_workspace(const SfvRbvae* r, int N);
+int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, const float* u, float noise_ratio,
+                 float temperature, int hard, float* h_out, float* z_out, uint32_t* codes, void* ws,
+                 size_t ws_bytes, cudaStream_t s);
+int resize_workspace(int B, int Hs, int Ws, int H, int W, size_t* bytes);
+int resize_normalise(const uint8_t* frames, int B, int Hs, int Ws, int H, int W, float* out_nchw,
+                     uint8_t* out_u8, void* ws, size_t ws_bytes, cudaStream_t s);
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SFV_ERR_CUDA, "no CUDA device: libsfv has no CPU fallback (%s)",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  int dev = 0, major = 0;
+  SFV_CUDA(cudaGetDevice(&dev));
+  SFV_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(SFV_ERR_CUDA, "libsfv is built for sm_100a only (device is sm_%d0)", major);
+  return 0;
+}
+}  // namespace sfv
+
+using namespace sfv;
+
+extern "C" {
+
+const char* sfv_version(void) { return "sfv-b200 0.1 (sm_100a)"; }
+const char* sfv_last_error(void) { return g_last_error.c_str(); }
+int sfv_device_ok(void) { return require_device() == 0 ? 1 : 0; }
+int64_t sfv_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t precision, SfvEncoder** out) {
+  if (!out || !tensors) return fail(SFV_ERR_INVALID, "encoder_create: null argument");
+  *out = nullptr;
+  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16)
+    return fail(SFV_ERR_INVALID, "encoder_create: unknown precision %d", precision);
+  SFV_TRY(require_device());
+  SfvEncoder* e = new (std::nothrow) SfvEncoder();
+  if (!e) return fail(SFV_ERR_INVALID, "out of host memory");
+  e->prec = precision;
+  e->fmt = fmt_of_precision(precision);
+  int st = encoder_build(e, tensors, n_tensors);
+  if (st != 0) { e->blob.release(); delete e; return st; }
+  *out = e;
+  return 0;
+}
+
+void sfv_encoder_destroy(SfvEncoder* e) {
+  if (!e) return;
+  e->blob.release();
+  delete e;
+}
+
+int sfv_encoder_precision(const SfvEncoder* e) { return e ? e->prec : SFV_ERR_INVALID; }
+
+int sfv_encoder_set_chunk(SfvEncoder* e, int32_t frames) {
+  if (!e || frames < 1) return fail(SFV_ERR_INVALID, "set_chunk: bad argument");
+  e->chunk = frames;
+  return 0;
+}
+
+int sfv_encoder_workspace_bytes(const SfvEncoder* e, int32_t B, int32_t H, int32_t W, size_t* bytes) {
+  if (!e || !bytes || B < 1 || H < 8 || W < 8) return fail(SFV_ERR_INVALID, "workspace_bytes: bad argument");
+  *bytes = encoder_workspace(e, B, H, W);
+  return 0;
+}
+
+int sfv_encoder_forward_nchw(SfvEncoder* e, const float* x, int32_t B, int32_t H, int32_t W, float* params,
+                             float* logvar, float* stdv, float* var, void* ws, size_t ws_bytes,
+                             float* const* taps, void* stream) {
+  if (!e || !x || !params || !logvar) return fail(SFV_ERR_INVALID, "encoder_forward: null argument");
+  return encoder_forward(e, x, SRC_NCHW_F32, B, H, W, params, logvar, stdv, var, ws, ws_bytes, taps,
+                         (cudaStream_t)stream);
+}
+
+int sfv_encoder_forward_u8(SfvEncoder* e, const uint8_t* frames, int32_t B, int32_t H, int32_t W, float* params,
+                           float* logvar, float* stdv, float* var, void* ws, size_t ws_bytes, void* stream) {
+  if (!e || !frames || !params || !logvar) return fail(SFV_ERR_INVALID, "encoder_forward_u8: null argument");
+  return encoder_forward(e, frames, SRC_NHWC_U8, B, H, W, params, logvar, stdv, var, ws, ws_bytes, nullptr,
+                         (cudaStream_t)stream);
+}
+
+int sfv_check_async_error(void* stream) { return tc_check_device_error((cudaStream_t)stream); }
+
+int sfv_posterior_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out,
+                         int64_t n, void* stream) {
+  if (!mean || !out || (noise && !logvar)) return fail(SFV_ERR_INVALID, "posterior_sample: null argument");
+  return launch_sample(mean, logvar, noise, scale, out, n, (cudaStream_t)stream);
+}
+
+int sfv_resize_workspace_bytes(int32_t B, int32_t Hs, int32_t Ws, int32_t H, int32_t W, size_t* bytes) {
+  return resize_workspace(B, Hs, Ws, H, W, bytes);
+}
+int sfv_resize_normalise(const uint8_t* frames, int32_t B, int32_t Hs, int32_t Ws, int32_t H, int32_t W,
+                         float* out_nchw, uint8_t* out_u8, void* ws, size_t ws_bytes, void* stream) {
+  return resize_normalise(frames, B, Hs, Ws, H, W, out_nchw, out_u8, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sfv_rbvae_create(const SfvTensor* tensors, int32_t n_tensors, int32_t in_channels, int32_t in_h, int32_t in_w,
+                     SfvRbvae** out) {
+  if (!out || !tensors) return fail(SFV_ERR_INVALID, "rbvae_create: null argument");
+  *out = nullptr;
+  if (in_channels < 1 || in_h < 1 || in_w < 1) return fail(SFV_ERR_INVALID, "rbvae_create: bad input shape");
+  SFV_TRY(require_device());
+  SfvRbvae* r = new (std::nothrow) SfvRbvae();
+  if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
+  r->in_channels = in_channels; r->in_h = in_h; r->in_w = in_w;
+  int st = rbvae_build(r, tensors, n_tensors);
+  if (st != 0) { r->blob.release(); delete r; return st; }
+  *out = r;
+  return 0;
+}
+void sfv_rbvae_destroy(SfvRbvae* r) {
+  if (!r) return;
+  r->blob.release();
+  delete r;
+}
+int sfv_rbvae_latent_dim(const SfvRbvae* r) { return r ? r->L : SFV_ERR_INVALID; }
+int sfv_rbvae_workspace_bytes(const SfvRbvae* r, int32_t N, size_t* bytes) {
+  if (!r || !bytes || N < 1) return fail(SFV_ERR_INVALID, "rbvae_workspace_bytes: bad argument");
+  *bytes = rbvae_workspace(r, N);
+  return 0;
+}
+int sfv_rbvae_encode(SfvRbvae* r, const float* x, int32_t B, int32_t T, float in_scale, const float* u,
+                     float noise_ratio, float temperature, int32_t hard, float* h_out, float* z_out,
+                     uint32_t* codes, void* ws, size_t ws_bytes, void* stream) {
+  if (!r || !x) return fail(SFV_ERR_INVALID, "rbvae_encode: null argument");
+  return rbvae_encode(r, x, B, T, in_scale, u, noise_ratio, temperature, hard, h_out, z_out, codes, ws, ws_bytes,
+                      (cudaStream_t)stream);
+}
+
+int sfv_hamming(const uint32_t* a, int32_t Na, const uint32_t* b, int32_t Nb, int32_t words, int32_t* out,
+                void* stream) {
+  if (!a || !b || !out) return fail(SFV_ERR_INVALID, "hamming: null argument");
+  return launch_hamming(a, Na, b, Nb, words, out, (cudaStream_t)stream);
+}
+
+// ---- single-operator entry points (test-only: allocate scratch internally, synchronous) ----
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  int get(size_t bytes, void** out) {
+    void* d = nullptr;
+    SFV_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+    p.push_back(d);
+    *out = d;
+    return 0;
+  }
+};
+
+int sfv_op_conv2d(const float* x, const float* host_w, const float* host_b, const float* residual, float* y,
+                  int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride,
+                  int32_t pad_lo, int32_t pad_hi, int32_t relu, int32_t precision, void* stream) {
+  SFV_TRY(require_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceBlob blob;
+  ConvW w;
+  const int fmt = fmt_of_precision(precision);
+  int st = make_conv_from_host(blob, host_w, host_b, Cout, Cin, ksize, fmt, precision != SFV_PREC_F32, &w);
+  if (st == 0) {
+    if (precision == SFV_PREC_F32) {
+      st = conv_f32(w, x, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, residual, y, relu, 1.f, s);
+    } else {
+      Scratch sc;
+      void* x16 = nullptr;
+      const long long n = (long long)N * H * W * Cin;
+      st = sc.get((size_t)n * 2, &x16);
+      if (st == 0) st = launch_f32_to_16(x, x16, n, fmt, s);
+      if (st == 0) st = conv_tc(w, fmt, x16, N, H, W, stride, pad_lo, pad_hi, residual, y, nullptr, relu, s);
+      if (st == 0) st = tc_check_device_error(s);
+      cudaStreamSynchronize(s);
+    }
+  }
+  if (st == 0 && cudaStreamSynchronize(s) != cudaSuccess) st = fail(SFV_ERR_CUDA, "op_conv2d: %s", cudaGetErrorString(cudaGetLastError()));
+  blob.release();
+  return st;
+}
+
+int sfv_op_group_norm(const float* x, const float* gamma, const float* beta, float* y, int32_t N, int32_t HW,
+                      int32_t C, int32_t groups, float eps, int32_t silu, void* stream) {
+  SFV_TRY(require_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  void* stats = nullptr;
+  SFV_TRY(sc.get(sizeof(double) * 2 * N * groups, &stats));
+  SFV_TRY(launch_gn_stats(x, 0, 0, N, HW, C, groups, (double*)stats, s));
+  SFV_TRY(launch_gn_apply(x, 0, (double*)stats, gamma, beta, y, 0, 0, N, HW, C, groups, eps, silu, s));
+  SFV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int sfv_op_attention(const float* q, const float* k, const float* v, float* out, int32_t N, int32_t L, int32_t C,
+                     float scale, int32_t precision, void* stream) {
+  SFV_TRY(require_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  void* S = nullptr;
+  SFV_TRY(sc.get((size_t)N * L * L * 4, &S));
+  if (precision == SFV_PREC_F32) {
+    SFV_TRY(attention_f32(q, k, v, out, (float*)S, N, L, C, scale, s));
+  } else {
+    // q, k in 16 bit; V^T through the same swapped-operand GEMM the encoder uses (identity weights)
+    SFV_CHECK(C % 64 == 0 && L % 8 == 0, "op_attention: needs C %% 64 == 0 and L %% 8 == 0");
+    const int fmt = fmt_of_precision(precision);
+    const long long n = (long long)N * L * C;
+    void *q16, *k16, *v16, *vT, *P, *O16;
+    SFV_TRY(sc.get(n * 2, &q16)); SFV_TRY(sc.get(n * 2, &k16)); SFV_TRY(sc.get(n * 2, &v16));
+    SFV_TRY(sc.get(n * 2, &vT)); SFV_TRY(sc.get((size_t)N * L * L * 2, &P)); SFV_TRY(sc.get(n * 2, &O16));
+    SFV_TRY(launch_f32_to_16(q, q16, n, fmt, s));
+    SFV_TRY(launch_f32_to_16(k, k16, n, fmt, s));
+    SFV_TRY(launch_f32_to_16(v, v16, n, fmt, s));
+    DeviceBlob blob;
+    ConvW ident;
+    std::vector<float> eye((size_t)C * C, 0.f);
+    for (int i = 0; i < C; ++i) eye[(size_t)i * C + i] = 1.f;
+    int st = make_conv_from_host(blob, eye.data(), nullptr, C, C, 1, fmt, true, &ident);
+    if (st == 0) st = vT_tc(ident, fmt, v16, vT, N, L, s);
+    if (st == 0) st = attention_tc(fmt, q16, C, k16, C, vT, nullptr, (float*)S, P, O16, N, L, C, scale, s);
+    // widen O back to fp32 with the igemm-free path: a 1x1 identity would round again, so convert directly
+    if (st == 0) st = launch_16_to_f32(O16, out, n, fmt, s);
+    if (st == 0) st = tc_check_device_error(s);
+    cudaStreamSynchronize(s);
+    blob.release();
+    if (st != 0) return st;
+  }
+  SFV_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // extern "C"

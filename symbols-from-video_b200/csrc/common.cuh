@@ -1,0 +1,164 @@
+// common.cuh -- shared host/device helpers for libsfv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <atomic>
+
+#include "../../include/sfv.h"
+
+namespace sfv {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<long long> g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define SFV_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return sfv::fail(SFV_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
+                       cudaGetErrorString(_e));                                     \
+  } while (0)
+
+#define SFV_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != 0) return _s;      \
+  } while (0)
+
+#define SFV_CHECK(cond, ...)                                    \
+  do {                                                          \
+    if (!(cond)) return sfv::fail(SFV_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// every kernel launch goes through this so the library can report a launch count
+#define SFV_LAUNCH_OK()                                                                    \
+  do {                                                                                     \
+    sfv::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return sfv::fail(SFV_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,             \
+                       cudaGetErrorString(_e));                                            \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// 16-bit operand formats of the tensor-core path.
+enum : int { FMT_F16 = 0, FMT_BF16 = 1 };   // == UMMA F16F32Format encoding
+inline int fmt_of_precision(int prec) { return prec == SFV_PREC_FP16 ? FMT_F16 : FMT_BF16; }
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ uint16_t f32_to_16(float v, int fmt) {
+  if (fmt == FMT_BF16) {
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&b);
+  } else {
+    // saturate instead of overflowing to inf: operands are bounded activations
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+__device__ __forceinline__ float f16_to_32(uint16_t v, int fmt) {
+  if (fmt == FMT_BF16) return __uint_as_float(((uint32_t)v) << 16);
+  __half h = *reinterpret_cast<__half*>(&v);
+  return __half2float(h);
+}
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, int fmt) {
+  return (uint32_t)f32_to_16(a, fmt) | ((uint32_t)f32_to_16(b, fmt) << 16);
+}
+
+// ---- bump allocator over the caller's workspace ----------------------------
+struct Arena {
+  char* base; size_t cap; size_t off;
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+  void* take(size_t bytes) {
+    size_t o = align_up(off, 1024);
+    off = o + bytes;
+    return base ? (void*)(base + o) : nullptr;   // base == nullptr: sizing pass
+  }
+  bool ok() const { return base == nullptr || off <= cap; }
+};
+
+// ---- igemm (CUDA-core fp32 implicit GEMM) -----------------------------------
+enum : int { SRC_NHWC_F32 = 0, SRC_NCHW_F32 = 1, SRC_NHWC_U8 = 2 };
+struct IgemmArgs {
+  const void* x; int src_kind;
+  const float* w;            // [K = kh*kw*Cin][Cout] fp32, or strided B
+  long long w_sk, w_sn;      // strides of B(k,n); conv: (Cout, 1)
+  long long w_batch;         // per-image stride of B (attention), 0 for conv
+  const float* bias;         // [Cout] or null
+  const float* residual;     // fp32, same layout as y, or null
+  float* y;                  // fp32 [N, Ho*Wo, ldy] (+ y_off)
+  void* y16;                 // optional 16-bit copy
+  int fmt16;
+  int N, H, W, Cin, Ho, Wo, Cout;
+  int ksize, stride, pad;    // pad = top/left padding (bottom/right implied by Ho/Wo)
+  int relu;
+  float alpha;               // scale applied to the accumulator before bias
+  float in_scale;            // scale applied to x on load
+  long long ldy;             // output row pitch (elements)
+  int nchw_out;              // write y as NCHW [N,Cout,Ho,Wo] instead
+};
+int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
+
+// ---- norm / elementwise ------------------------------------------------------
+// stats: double [N][G][2] accumulators (sum, sumsq) -- zeroed by the caller/kernel.
+int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int C, int G,
+                    double* stats, cudaStream_t s);
+int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma,
+                    const float* beta, void* y, int y_is16, int fmt, int N, long long HW, int C,
+                    int G, float eps, int silu, cudaStream_t s);
+int launch_zero(void* p, size_t bytes, cudaStream_t s);
+int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t s);
+int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s);
+int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,
+                        cudaStream_t s);
+int launch_head(const float* moments_nhwc8, float* params, float* logvar, float* stdv, float* var,
+                int N, int HW, cudaStream_t s);
+int launch_sample(const float* mean, const float* logvar, const float* noise, float scale,
+                  float* out, long long n, cudaStream_t s);
+int launch_lstm_code(const float* logits, int B, int T, int L, int layers,
+                     const float* w_ih, const float* w_hh, const float* bias,
+                     const float* u, float noise_ratio, float temperature, int hard,
+                     float* h_out, float* z_out, uint32_t* codes, cudaStream_t s);
+int launch_fc(const float* x, const float* w, const float* bias, float* y, int N, long long K,
+              int L, float* partial, int splits, cudaStream_t s);
+int launch_hamming(const uint32_t* a, int Na, const uint32_t* b, int Nb, int words, int* out,
+                   cudaStream_t s);
+
+// ---- tcgen05 conv / GEMM -----------------------------------------------------
+struct TcTap { int o[5]; };
+struct TcGemmArgs {
+  // A operand: 16-bit tensor described for TMA as up to 5 dims (dim0 = K/channels).
+  const void* a; int a_rank;
+  unsigned long long a_dims[5];
+  unsigned long long a_strides[5];   // bytes; strides[0] ignored (contiguous)
+  unsigned a_box[5];                 // box[0] = 64
+  int dim_x, dim_y, dim_n;           // which A dims the tile x / y / image coordinates feed (-1: none)
+  // B operand: [batch][Nrows][K] 16-bit, K contiguous
+  const void* b; unsigned long long b_rows, b_k; unsigned long long b_row_stride, b_batch_stride;
+  int b_batched;
+  int ntaps; TcTap taps[9]; int tap_k[9];  // tap_k: k offset in B for this tap
+  int kchunks;                       // 64-wide K chunks per tap
+  // tiling of the output
+  int BW, BH;                        // tile = BH rows x BW cols (BH*BW == 128)
+  int Wo, Ho, Nimg, Cout;
+  int block_n;
+  // epilogue
+  float alpha; const float* bias; const float* residual;
+  float* out_f32; void* out_16; int fmt; long long ldo; int relu;
+  double* gn_stats; int gn_group;    // optional fused GroupNorm partial sums
+};
+int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s);
+int tc_check_device_error(cudaStream_t s);   // sync + read the watchdog flag
+
+}  // namespace sfv

@@ -1,0 +1,523 @@
+// encoder.cu -- KL-f8 encoder handle: weight ingestion/repacking and the forward
+// schedule.  Mirrors Encoder.forward (ldm/modules/diffusionmodules/model.py:434-459),
+// ResnetBlock.forward (:121-141), Downsample.forward (:72-79), AttnBlock.forward
+// (:178-202) and AutoencoderKL.encode (ldm/models/autoencoder.py:324-328).
+//
+// Data layout in HBM (per chunk of Bc frames):
+//   x stream      fp32 NHWC   (residual stream; never rounded to 16 bit)
+//   operands      16-bit NHWC (bf16 or fp16): GroupNorm+SiLU outputs, conv1 outputs,
+//                 and a 16-bit copy of x where a conv consumes x directly
+//                 (downsample, nin_shortcut)
+//   GN statistics fp64 [Bc][32][2]
+// In fp32 check mode the operand buffers hold fp32 and every GEMM runs on the
+// CUDA-core kernel.
+#include "common.cuh"
+#include "encoder.h"
+#include <math.h>
+#include <string.h>
+
+namespace sfv {
+
+// ------------------------------------------------------------------ weights
+static const SfvTensor* find_tensor(const SfvTensor* t, int n, const std::string& name) {
+  for (int i = 0; i < n; ++i)
+    if (t[i].name && name == t[i].name) return &t[i];
+  return nullptr;
+}
+
+static uint16_t host_to_16(float v, int fmt) {
+  if (fmt == FMT_BF16) {
+    uint32_t u; memcpy(&u, &v, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+  }
+  __half h = __float2half_rn(v);
+  uint16_t o; memcpy(&o, &h, 2);
+  return o;
+}
+
+int DeviceBlob::upload(const void* host, size_t bytes, void** out) {
+  void* d = nullptr;
+  SFV_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+  allocs.push_back(d);
+  if (bytes) SFV_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+void DeviceBlob::release() {
+  for (void* p : allocs) cudaFree(p);
+  allocs.clear();
+}
+
+// OIHW fp32 host weights -> (a) fp32 [K][Cout] for the CUDA-core kernel,
+// (b) 16-bit [Cout_pad][K] K-major rows for UMMA; k = (r*ks + s)*Cin + ci.
+int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
+                        int fmt, bool want16, ConvW* out) {
+  out->Cin = Cin; out->Cout = Cout; out->ks = ks;
+  const int K = ks * ks * Cin;
+  out->cout_pad = (Cout + 15) / 16 * 16;
+  std::vector<float> w32((size_t)K * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int i = 0; i < Cin; ++i)
+      for (int t = 0; t < ks * ks; ++t)
+        w32[((size_t)t * Cin + i) * Cout + o] = w[((size_t)o * Cin + i) * ks * ks + t];
+  SFV_TRY(blob.upload(w32.data(), w32.size() * 4, (void**)&out->w32));
+  std::vector<float> bias(out->cout_pad, 0.f);
+  if (b) for (int o = 0; o < Cout; ++o) bias[o] = b[o];
+  SFV_TRY(blob.upload(bias.data(), bias.size() * 4, (void**)&out->bias));
+  out->w16 = nullptr;
+  if (want16 && Cin % 64 == 0) {
+    std::vector<uint16_t> w16((size_t)out->cout_pad * K, 0);
+    for (int o = 0; o < Cout; ++o)
+      for (int i = 0; i < Cin; ++i)
+        for (int t = 0; t < ks * ks; ++t)
+          w16[(size_t)o * K + (size_t)t * Cin + i] = host_to_16(w[((size_t)o * Cin + i) * ks * ks + t], fmt);
+    SFV_TRY(blob.upload(w16.data(), w16.size() * 2, &out->w16));
+  }
+  return 0;
+}
+
+static int get_conv(DeviceBlob& blob, const SfvTensor* t, int n, const std::string& name, int Cout,
+                    int Cin, int ks, int fmt, bool want16, ConvW* out) {
+  const SfvTensor* w = find_tensor(t, n, name + ".weight");
+  const SfvTensor* b = find_tensor(t, n, name + ".bias");
+  if (!w || !b) return fail(SFV_ERR_MISSING_KEY, "missing state-dict key %s.{weight,bias}", name.c_str());
+  if (w->ndim != 4 || w->shape[0] != Cout || w->shape[1] != Cin || w->shape[2] != ks || w->shape[3] != ks ||
+      b->shape[0] != Cout)
+    return fail(SFV_ERR_MISSING_KEY, "%s: expected [%d,%d,%d,%d]", name.c_str(), Cout, Cin, ks, ks);
+  return make_conv_from_host(blob, w->host_data, b->host_data, Cout, Cin, ks, fmt, want16, out);
+}
+
+static int get_norm(DeviceBlob& blob, const SfvTensor* t, int n, const std::string& name, int C, NormW* out) {
+  const SfvTensor* w = find_tensor(t, n, name + ".weight");
+  const SfvTensor* b = find_tensor(t, n, name + ".bias");
+  if (!w || !b || w->shape[0] != C || b->shape[0] != C)
+    return fail(SFV_ERR_MISSING_KEY, "missing/mis-shaped state-dict key %s.{weight,bias} [%d]", name.c_str(), C);
+  out->C = C;
+  SFV_TRY(blob.upload(w->host_data, (size_t)C * 4, (void**)&out->gamma));
+  SFV_TRY(blob.upload(b->host_data, (size_t)C * 4, (void**)&out->beta));
+  return 0;
+}
+
+static int get_res(DeviceBlob& blob, const SfvTensor* t, int n, const std::string& name, int Cin, int Cout,
+                   int fmt, bool want16, ResW* r) {
+  SFV_TRY(get_norm(blob, t, n, name + ".norm1", Cin, &r->n1));
+  SFV_TRY(get_conv(blob, t, n, name + ".conv1", Cout, Cin, 3, fmt, want16, &r->c1));
+  SFV_TRY(get_norm(blob, t, n, name + ".norm2", Cout, &r->n2));
+  SFV_TRY(get_conv(blob, t, n, name + ".conv2", Cout, Cout, 3, fmt, want16, &r->c2));
+  r->has_nin = Cin != Cout;
+  if (r->has_nin) SFV_TRY(get_conv(blob, t, n, name + ".nin_shortcut", Cout, Cin, 1, fmt, want16, &r->nin));
+  return 0;
+}
+
+int encoder_build(SfvEncoder* e, const SfvTensor* t, int n) {
+  const bool tc = e->prec != SFV_PREC_F32;
+  const int fmt = e->fmt;
+  // accept both "encoder.x" and "first_stage_model.encoder.x" (get_percep_embeddings.py:34-39)
+  std::string pre = "";
+  if (!find_tensor(t, n, "encoder.conv_in.weight") && find_tensor(t, n, "first_stage_model.encoder.conv_in.weight"))
+    pre = "first_stage_model.";
+  const std::string p = pre + "encoder.";
+  static const int mult[4] = {1, 2, 4, 4};
+  SFV_TRY(get_conv(e->blob, t, n, p + "conv_in", 128, 3, 3, fmt, false, &e->conv_in));
+  int cin = 128;
+  for (int l = 0; l < 4; ++l) {
+    const int cout = 128 * mult[l];
+    for (int b = 0; b < 2; ++b) {
+      SFV_TRY(get_res(e->blob, t, n, p + "down." + std::to_string(l) + ".block." + std::to_string(b), cin, cout,
+                      fmt, tc, &e->down[l][b]));
+      cin = cout;
+    }
+    if (l != 3)
+      SFV_TRY(get_conv(e->blob, t, n, p + "down." + std::to_string(l) + ".downsample.conv", cin, cin, 3, fmt, tc,
+                       &e->ds[l]));
+  }
+  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_1", 512, 512, fmt, tc, &e->mid1));
+  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_2", 512, 512, fmt, tc, &e->mid2));
+  SFV_TRY(get_norm(e->blob, t, n, p + "mid.attn_1.norm", 512, &e->attn_norm));
+  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.q", 512, 512, 1, fmt, tc, &e->q));
+  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.k", 512, 512, 1, fmt, tc, &e->k));
+  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.v", 512, 512, 1, fmt, tc, &e->v));
+  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.proj_out", 512, 512, 1, fmt, tc, &e->proj));
+  {  // fused q|k projection: one GEMM with N = 1024
+    const SfvTensor* qw = find_tensor(t, n, p + "mid.attn_1.q.weight");
+    const SfvTensor* kw = find_tensor(t, n, p + "mid.attn_1.k.weight");
+    const SfvTensor* qb = find_tensor(t, n, p + "mid.attn_1.q.bias");
+    const SfvTensor* kb = find_tensor(t, n, p + "mid.attn_1.k.bias");
+    std::vector<float> w(1024 * 512), b(1024);
+    memcpy(w.data(), qw->host_data, 512 * 512 * 4);
+    memcpy(w.data() + 512 * 512, kw->host_data, 512 * 512 * 4);
+    memcpy(b.data(), qb->host_data, 512 * 4);
+    memcpy(b.data() + 512, kb->host_data, 512 * 4);
+    SFV_TRY(make_conv_from_host(e->blob, w.data(), b.data(), 1024, 512, 1, fmt, tc, &e->qk));
+  }
+  SFV_TRY(get_norm(e->blob, t, n, p + "norm_out", 512, &e->norm_out));
+  {  // conv_out (3x3, 512->8) with quant_conv (1x1, 8->8) folded in:
+     // W'[o] = sum_m Wq[o][m] Wc[m],  b' = Wq bc + bq   (autoencoder.py:325-326)
+    const SfvTensor* cw = find_tensor(t, n, p + "conv_out.weight");
+    const SfvTensor* cb = find_tensor(t, n, p + "conv_out.bias");
+    const SfvTensor* qw = find_tensor(t, n, pre + "quant_conv.weight");
+    const SfvTensor* qb = find_tensor(t, n, pre + "quant_conv.bias");
+    if (!cw || !cb || !qw || !qb || cw->shape[0] != 8 || cw->shape[1] != 512 || qw->shape[0] != 8 || qw->shape[1] != 8)
+      return fail(SFV_ERR_MISSING_KEY, "missing/mis-shaped conv_out / quant_conv");
+    const int per = 512 * 9;
+    std::vector<float> w((size_t)8 * per), b(8);
+    for (int o = 0; o < 8; ++o) {
+      for (int j = 0; j < per; ++j) {
+        double a = 0;
+        for (int m = 0; m < 8; ++m) a += (double)qw->host_data[o * 8 + m] * cw->host_data[(size_t)m * per + j];
+        w[(size_t)o * per + j] = (float)a;
+      }
+      double a = qb->host_data[o];
+      for (int m = 0; m < 8; ++m) a += (double)qw->host_data[o * 8 + m] * cb->host_data[m];
+      b[o] = (float)a;
+    }
+    SFV_TRY(make_conv_from_host(e->blob, w.data(), b.data(), 8, 512, 3, fmt, tc, &e->conv_out));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ op dispatch
+static void choose_tile(int Wo, int Ho, int* BW, int* BH) {
+  double best = -1; int bw = 128;
+  for (int w = 128; w >= 8; w >>= 1) {
+    const int h = 128 / w;
+    const double util = ((double)Wo * Ho) / ((double)ceil_div(Wo, w) * w * ceil_div(Ho, h) * h);
+    if (util > best + 1e-9) { best = util; bw = w; }
+  }
+  *BW = bw; *BH = 128 / bw;
+}
+
+static int pick_block_n(int cout_pad) {
+  if (cout_pad % 256 == 0) return 256;
+  if (cout_pad % 128 == 0) return 128;
+  if (cout_pad % 64 == 0) return 64;
+  if (cout_pad % 32 == 0) return 32;
+  return 16;
+}
+
+// conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
+int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
+            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s) {
+  SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
+  const int ks = w.ks, Cin = w.Cin;
+  int Ho, Wo;
+  TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.a = in16; a.fmt = fmt;
+  if (stride == 1) {
+    Ho = H + pad_lo + pad_hi - ks + 1; Wo = W + pad_lo + pad_hi - ks + 1;
+    choose_tile(Wo, Ho, &a.BW, &a.BH);
+    a.a_rank = 4;
+    a.a_dims[0] = Cin; a.a_dims[1] = W; a.a_dims[2] = H; a.a_dims[3] = N;
+    a.a_strides[1] = (unsigned long long)Cin * 2; a.a_strides[2] = a.a_strides[1] * W; a.a_strides[3] = a.a_strides[2] * H;
+    a.a_box[0] = 64; a.a_box[1] = a.BW; a.a_box[2] = a.BH; a.a_box[3] = 1;
+    a.dim_x = 1; a.dim_y = 2; a.dim_n = 3;
+    a.ntaps = ks * ks;
+    for (int r = 0; r < ks; ++r)
+      for (int c = 0; c < ks; ++c) {
+        TcTap& t = a.taps[r * ks + c];
+        t.o[1] = c - pad_lo; t.o[2] = r - pad_lo;
+        a.tap_k[r * ks + c] = (r * ks + c) * Cin;
+      }
+  } else {
+    SFV_CHECK(stride == 2 && H % 2 == 0 && W % 2 == 0, "conv_tc: stride-2 needs even H, W");
+    Ho = (H + pad_lo + pad_hi - ks) / 2 + 1; Wo = (W + pad_lo + pad_hi - ks) / 2 + 1;
+    choose_tile(Wo, Ho, &a.BW, &a.BH);
+    a.a_rank = 5;
+    a.a_dims[0] = 2ull * Cin; a.a_dims[1] = W / 2; a.a_dims[2] = 2; a.a_dims[3] = H / 2; a.a_dims[4] = N;
+    a.a_strides[1] = 2ull * Cin * 2; a.a_strides[2] = (unsigned long long)W * Cin * 2;
+    a.a_strides[3] = 2ull * W * Cin * 2; a.a_strides[4] = (unsigned long long)H * W * Cin * 2;
+    a.a_box[0] = 64; a.a_box[1] = a.BW; a.a_box[2] = 1; a.a_box[3] = a.BH; a.a_box[4] = 1;
+    a.dim_x = 1; a.dim_y = 3; a.dim_n = 4;
+    a.ntaps = ks * ks;
+    for (int r = 0; r < ks; ++r)
+      for (int c = 0; c < ks; ++c) {
+        TcTap& t = a.taps[r * ks + c];
+        const int qx = c - pad_lo, qy = r - pad_lo;
+        const int px = qx & 1, py = qy & 1;
+        t.o[0] = px * Cin; t.o[1] = (qx - px) / 2; t.o[2] = py; t.o[3] = (qy - py) / 2;
+        a.tap_k[r * ks + c] = (r * ks + c) * Cin;
+      }
+  }
+  a.kchunks = Cin / 64;
+  a.b = w.w16; a.b_rows = w.cout_pad; a.b_k = (unsigned long long)ks * ks * Cin;
+  a.b_row_stride = a.b_k * 2; a.b_batched = 0;
+  a.Wo = Wo; a.Ho = Ho; a.Nimg = N; a.Cout = w.Cout;
+  a.block_n = pick_block_n(w.cout_pad);
+  a.alpha = 1.f; a.bias = w.bias; a.residual = residual;
+  a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
+  return launch_tc_gemm(a, s);
+}
+
+int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
+             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s) {
+  IgemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = in; a.src_kind = src_kind; a.w = w.w32; a.w_sk = w.Cout; a.w_sn = 1; a.w_batch = 0;
+  a.bias = w.bias; a.residual = residual; a.y = out;
+  a.N = N; a.H = H; a.W = W; a.Cin = w.Cin; a.Cout = w.Cout;
+  a.ksize = w.ks; a.stride = stride; a.pad = pad_lo;
+  a.Ho = (H + pad_lo + pad_hi - w.ks) / stride + 1;
+  a.Wo = (W + pad_lo + pad_hi - w.ks) / stride + 1;
+  a.relu = relu; a.alpha = 1.f; a.in_scale = in_scale; a.ldy = w.Cout;
+  return launch_igemm_f32(a, s);
+}
+
+// ------------------------------------------------------------------ forward
+namespace {
+
+struct Plan {
+  float *xa, *xb;
+  void *oa, *ob, *x16, *x16b;
+  double* stats;
+  float* S; void* P; float* moments;
+  int attn_chunk;
+};
+
+void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
+  const size_t E0 = (size_t)Bc * H * W * 128;
+  const size_t osz = tc ? 2 : 4;
+  const size_t L = (size_t)(H / 8) * (W / 8);
+  p->xa = (float*)ar.take(E0 * 4);
+  p->xb = (float*)ar.take(E0 * 4);
+  p->oa = ar.take(E0 * osz);
+  p->ob = ar.take(E0 * osz);
+  p->x16 = tc ? ar.take(E0 * osz) : nullptr;        // 16-bit copy of x feeding a downsample; V^T in attention
+  p->x16b = tc ? ar.take(E0 / 4 * osz) : nullptr;   // 16-bit copy of a downsample output feeding nin_shortcut
+  p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
+  const size_t per_img = L * L * (tc ? 6 : 4);
+  size_t na = (size_t)(1536ull << 20) / (per_img ? per_img : 1);
+  if (na < 1) na = 1;
+  if (na > (size_t)Bc) na = Bc;
+  p->attn_chunk = (int)na;
+  p->S = (float*)ar.take(na * L * L * 4);
+  p->P = tc ? ar.take(na * L * L * 2) : nullptr;
+  p->moments = (float*)ar.take((size_t)Bc * L * 8 * 4);
+}
+
+struct Fwd {
+  SfvEncoder* e; cudaStream_t s; bool tc; int fmt; Plan pl; int N;
+
+  int gn(const NormW& nw, const void* in, bool in_is16, long long HW, int silu, void* out) {
+    SFV_TRY(launch_gn_stats(in, in_is16, fmt, N, HW, nw.C, 32, pl.stats, s));
+    return launch_gn_apply(in, in_is16, pl.stats, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s);
+  }
+  // operand-typed input -> fp32 stream and/or operand-typed output
+  int conv(const ConvW& w, const void* in_op, int H, int W, int stride, const float* residual,
+           float* out_stream, void* out_op) {
+    // 3x3 s1: pad 1/1;  1x1: none;  3x3 s2 (Downsample): zero pad right/bottom only (model.py:75-77)
+    const int pad_lo = (w.ks == 3 && stride == 1) ? 1 : 0;
+    const int pad_hi = (w.ks == 3) ? 1 : 0;
+    if (tc) return conv_tc(w, fmt, in_op, N, H, W, stride, pad_lo, pad_hi, residual, out_stream, out_op, 0, s);
+    float* y = out_stream ? out_stream : (float*)out_op;
+    return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, residual, y, 0, 1.f, s);
+  }
+
+  // x: fp32 stream (C=Cin), x_op: operand copy of x (needed only when r.has_nin).
+  // Writes the block output to `xo` (and its operand copy to pl.x16 if want_copy).
+  int resblock(const ResW& r, const float* x, const void* x_op, int H, int W, float* xo, bool want_copy,
+               const void** xo_op) {
+    const long long HW = (long long)H * W;
+    SFV_TRY(gn(r.n1, x, false, HW, 1, pl.oa));
+    SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob));
+    SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa));
+    const float* res = x;
+    if (r.has_nin) {
+      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr));
+      res = xo;
+    }
+    void* copy = (tc && want_copy) ? pl.x16 : nullptr;
+    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy));
+    *xo_op = tc ? copy : (const void*)xo;
+    return 0;
+  }
+
+  int attention(const float* x, int h, int w, float* xo) {
+    const int L = h * w;
+    const int C = 512;
+    const float scale = 1.0f / sqrtf((float)C);
+    SFV_TRY(gn(e->attn_norm, x, false, L, 0, pl.oa));       // hn (no SiLU)
+    if (tc) {
+      SFV_CHECK(L % 8 == 0, "tensor-core attention needs (H/8)*(W/8) %% 8 == 0 (got %d)", L);
+      uint16_t* qk = (uint16_t*)pl.ob;                      // [N][L][1024]: q | k
+      uint16_t* vT = (uint16_t*)pl.x16;                     // [N][512][L]
+      SFV_TRY(conv_tc(e->qk, fmt, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s));
+      // bias b_v is added after P V (rows of P sum to 1)
+      SFV_TRY(vT_tc(e->v, fmt, pl.oa, vT, N, L, s));
+      uint16_t* O = (uint16_t*)pl.oa;                       // [N][L][512]  (hn is dead after the two GEMMs above)
+      for (int n0 = 0; n0 < N; n0 += pl.attn_chunk) {
+        const int nn = (N - n0) < pl.attn_chunk ? (N - n0) : pl.attn_chunk;
+        SFV_TRY(attention_tc(fmt, qk + (size_t)n0 * L * 1024, 1024, qk + (size_t)n0 * L * 1024 + 512, 1024,
+                             vT + (size_t)n0 * C * L, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
+                             scale, s));
+      }
+      SFV_TRY(conv_tc(e->proj, fmt, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s));
+    } else {
+      float* q = (float*)pl.ob;
+      float* k = q + (size_t)N * L * C;
+      float* v = k + (size_t)N * L * C;
+      SFV_TRY(conv_f32(e->q, pl.oa, SRC_NHWC_F32, N, h, w, 1, 0, 0, nullptr, q, 0, 1.f, s));
+      SFV_TRY(conv_f32(e->k, pl.oa, SRC_NHWC_F32, N, h, w, 1, 0, 0, nullptr, k, 0, 1.f, s));
+      SFV_TRY(conv_f32(e->v, pl.oa, SRC_NHWC_F32, N, h, w, 1, 0, 0, nullptr, v, 0, 1.f, s));
+      float* O = (float*)pl.oa;
+      for (int n0 = 0; n0 < N; n0 += pl.attn_chunk) {
+        const int nn = (N - n0) < pl.attn_chunk ? (N - n0) : pl.attn_chunk;
+        SFV_TRY(attention_f32(q + (size_t)n0 * L * C, k + (size_t)n0 * L * C, v + (size_t)n0 * L * C,
+                              O + (size_t)n0 * L * C, pl.S, nn, L, C, scale, s));
+      }
+      SFV_TRY(conv_f32(e->proj, O, SRC_NHWC_F32, N, h, w, 1, 0, 0, x, xo, 0, 1.f, s));
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+// Tensor-core attention core for a chunk of images whose score matrices fit S/P:
+//   S = scale * Q K^T (fp32) ; P = softmax(S) (16-bit) ; O = P V + b_v (16-bit)
+// q16/k16: [N][L][*] rows with pitch q_ld/k_ld elements; vT16: [N][C][L].
+int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long long k_ld,
+                 const void* vT16, const float* v_bias, float* S, void* P, void* O16, int N, int L, int C,
+                 float scale, cudaStream_t s) {
+  {
+    TcGemmArgs a; memset(&a, 0, sizeof(a));
+    a.a = q16; a.fmt = fmt; a.a_rank = 3;
+    a.a_dims[0] = C; a.a_dims[1] = L; a.a_dims[2] = N;
+    a.a_strides[1] = (unsigned long long)q_ld * 2; a.a_strides[2] = (unsigned long long)L * q_ld * 2;
+    a.a_box[0] = 64; a.a_box[1] = 128; a.a_box[2] = 1;
+    a.dim_x = 1; a.dim_y = -1; a.dim_n = 2;
+    a.ntaps = 1; a.kchunks = ceil_div(C, 64);
+    a.b = k16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)k_ld * 2;
+    a.b_batch_stride = (unsigned long long)L * k_ld * 2; a.b_batched = 1;
+    a.BW = 128; a.BH = 1; a.Wo = L; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
+    a.alpha = scale; a.out_f32 = S; a.ldo = L;
+    SFV_TRY(launch_tc_gemm(a, s));
+  }
+  SFV_TRY(launch_softmax_rows(S, P, 1, fmt, (long long)N * L, L, s));
+  {
+    TcGemmArgs a; memset(&a, 0, sizeof(a));
+    a.a = P; a.fmt = fmt; a.a_rank = 3;
+    a.a_dims[0] = L; a.a_dims[1] = L; a.a_dims[2] = N;
+    a.a_strides[1] = (unsigned long long)L * 2; a.a_strides[2] = (unsigned long long)L * L * 2;
+    a.a_box[0] = 64; a.a_box[1] = 128; a.a_box[2] = 1;
+    a.dim_x = 1; a.dim_y = -1; a.dim_n = 2;
+    a.ntaps = 1; a.kchunks = ceil_div(L, 64);
+    a.b = vT16; a.b_rows = C; a.b_k = L; a.b_row_stride = (unsigned long long)L * 2;
+    a.b_batch_stride = (unsigned long long)C * L * 2; a.b_batched = 1;
+    a.BW = 128; a.BH = 1; a.Wo = L; a.Ho = 1; a.Nimg = N; a.Cout = C; a.block_n = pick_block_n(C);
+    a.alpha = 1.f; a.bias = v_bias; a.out_16 = O16; a.ldo = C;
+    SFV_TRY(launch_tc_gemm(a, s));
+  }
+  return 0;
+}
+
+// V^T[n][c][token] = sum_k Wv[c][k] x[n][token][k]: the value projection computed
+// directly in the K-major layout the P V GEMM needs as its B operand.
+int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cudaStream_t s) {
+  const int C = v.Cin;
+  TcGemmArgs a; memset(&a, 0, sizeof(a));
+  a.a = v.w16; a.fmt = fmt; a.a_rank = 2;
+  a.a_dims[0] = C; a.a_dims[1] = v.cout_pad; a.a_strides[1] = (unsigned long long)C * 2;
+  a.a_box[0] = 64; a.a_box[1] = 128;
+  a.dim_x = 1; a.dim_y = -1; a.dim_n = -1;
+  a.ntaps = 1; a.kchunks = C / 64;
+  a.b = x16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)C * 2;
+  a.b_batch_stride = (unsigned long long)L * C * 2; a.b_batched = 1;
+  a.BW = 128; a.BH = 1; a.Wo = v.Cout; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
+  a.alpha = 1.f; a.out_16 = vT16; a.ldo = L;
+  return launch_tc_gemm(a, s);
+}
+
+// fp32 attention core on the CUDA-core GEMM: S = scale q k^T, softmax (in place), O = P v
+int attention_f32(const float* q, const float* k, const float* v, float* O, float* S, int N, int L, int C,
+                  float scale, cudaStream_t s) {
+  IgemmArgs a; memset(&a, 0, sizeof(a));
+  a.x = q; a.src_kind = SRC_NHWC_F32; a.w = k; a.w_sk = 1; a.w_sn = C; a.w_batch = (long long)L * C;
+  a.y = S; a.N = N; a.H = 1; a.W = L; a.Cin = C; a.Ho = 1; a.Wo = L; a.Cout = L;
+  a.ksize = 1; a.stride = 1; a.pad = 0; a.alpha = scale; a.in_scale = 1.f; a.ldy = L;
+  SFV_TRY(launch_igemm_f32(a, s));
+  SFV_TRY(launch_softmax_rows(S, S, 0, 0, (long long)N * L, L, s));
+  memset(&a, 0, sizeof(a));
+  a.x = S; a.src_kind = SRC_NHWC_F32; a.w = v; a.w_sk = C; a.w_sn = 1; a.w_batch = (long long)L * C;
+  a.y = O; a.N = N; a.H = 1; a.W = L; a.Cin = L; a.Ho = 1; a.Wo = L; a.Cout = C;
+  a.ksize = 1; a.stride = 1; a.pad = 0; a.alpha = 1.f; a.in_scale = 1.f; a.ldy = C;
+  return launch_igemm_f32(a, s);
+}
+
+size_t encoder_workspace(const SfvEncoder* e, int B, int H, int W) {
+  const int Bc = B < e->chunk ? B : e->chunk;
+  Arena ar(nullptr, 0);
+  Plan p;
+  make_plan(e->prec != SFV_PREC_F32, Bc, H, W, ar, &p);
+  return ar.off + 1024;
+}
+
+int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, int W, float* params,
+                    float* logvar, float* stdv, float* var, void* ws, size_t ws_bytes, float* const* taps,
+                    cudaStream_t s) {
+  SFV_CHECK(B >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "encoder: H, W must be multiples of 8 (got %dx%d)", H, W);
+  SFV_CHECK(ws != nullptr && ws_bytes >= encoder_workspace(e, B, H, W), "encoder: workspace too small (%zu < %zu)",
+            ws_bytes, encoder_workspace(e, B, H, W));
+  const bool tc = e->prec != SFV_PREC_F32;
+  const int chunk = B < e->chunk ? B : e->chunk;
+  const int h8 = H / 8, w8 = W / 8;
+  const long long L = (long long)h8 * w8;
+  static const long long tapC[SFV_NUM_TAPS] = {128, 128, 128, 256, 256, 512, 512, 512, 512, 128, 256, 512, 512, 512, 512, 8};
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    Fwd f; f.e = e; f.s = s; f.tc = tc; f.fmt = e->fmt; f.N = (B - b0) < chunk ? (B - b0) : chunk;
+    Arena ar(ws, ws_bytes);
+    make_plan(tc, chunk, H, W, ar, &f.pl);
+    const int N = f.N;
+    auto tap = [&](int idx, const float* src, int hh, int ww) -> int {
+      if (!taps || !taps[idx]) return 0;
+      const size_t per = (size_t)hh * ww * tapC[idx];
+      SFV_CUDA(cudaMemcpyAsync(taps[idx] + (size_t)b0 * per, src, per * N * 4, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    };
+    // conv_in straight from the boundary layout (fp32 NCHW or uint8 HWC)
+    const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
+    SFV_TRY(conv_f32(e->conv_in, xin, src_kind, N, H, W, 1, 1, 1, nullptr, f.pl.xa, 0, 1.f, s));
+    SFV_TRY(tap(0, f.pl.xa, H, W));
+    float* cur = f.pl.xa; float* oth = f.pl.xb;
+    const void* cur_op = tc ? nullptr : (const void*)cur;
+    int ch = H, cw = W;
+    for (int l = 0; l < 4; ++l) {
+      for (int b = 0; b < 2; ++b) {
+        // the block's output is consumed directly by a conv (downsample) only after block 1 of levels 0..2
+        const bool want_copy = (b == 1 && l != 3);
+        SFV_TRY(f.resblock(e->down[l][b], cur, cur_op, ch, cw, oth, want_copy, &cur_op));
+        std::swap(cur, oth);
+        SFV_TRY(tap(1 + l * 2 + b, cur, ch, cw));
+      }
+      if (l != 3) {
+        // downsample output feeds down.(l+1).block.0, whose nin_shortcut (levels 1, 2) reads x directly
+        const bool want_copy = tc && e->down[l + 1][0].has_nin;
+        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr));
+        ch /= 2; cw /= 2;
+        std::swap(cur, oth);
+        cur_op = tc ? (want_copy ? (const void*)f.pl.x16b : nullptr) : (const void*)cur;
+        SFV_TRY(tap(9 + l, cur, ch, cw));
+      }
+    }
+    SFV_TRY(f.resblock(e->mid1, cur, cur_op, ch, cw, oth, false, &cur_op));
+    std::swap(cur, oth);
+    SFV_TRY(tap(12, cur, ch, cw));
+    SFV_TRY(f.attention(cur, ch, cw, oth));
+    std::swap(cur, oth);
+    SFV_TRY(tap(13, cur, ch, cw));
+    SFV_TRY(f.resblock(e->mid2, cur, nullptr, ch, cw, oth, false, &cur_op));
+    std::swap(cur, oth);
+    SFV_TRY(tap(14, cur, ch, cw));
+    SFV_TRY(f.gn(e->norm_out, cur, false, L, 1, f.pl.oa));
+    SFV_TRY(f.conv(e->conv_out, f.pl.oa, ch, cw, 1, nullptr, f.pl.moments, nullptr));
+    SFV_TRY(tap(15, f.pl.moments, ch, cw));
+    SFV_TRY(launch_head(f.pl.moments, params + (size_t)b0 * 8 * L, logvar + (size_t)b0 * 4 * L,
+                        stdv ? stdv + (size_t)b0 * 4 * L : nullptr, var ? var + (size_t)b0 * 4 * L : nullptr, N,
+                        (int)L, s));
+  }
+  return 0;
+}
+
+}  // namespace sfv

@@ -1,0 +1,61 @@
+// encoder.h -- handle structs shared by encoder.cu / rbvae.cu / api.cu
+#pragma once
+#include "common.cuh"
+
+namespace sfv {
+
+struct DeviceBlob {
+  std::vector<void*> allocs;
+  int upload(const void* host, size_t bytes, void** out);
+  void release();
+};
+
+struct ConvW {
+  int Cin = 0, Cout = 0, ks = 0, cout_pad = 0;
+  float* w32 = nullptr;    // [ks*ks*Cin][Cout] fp32 (CUDA-core kernel)
+  void* w16 = nullptr;     // [cout_pad][ks*ks*Cin] 16-bit, K-major (UMMA B operand)
+  float* bias = nullptr;   // [cout_pad]
+};
+struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
+struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
+
+int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
+                        int fmt, bool want16, ConvW* out);
+int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
+            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s);
+int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
+             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s);
+int attention_f32(const float* q, const float* k, const float* v, float* O, float* S, int N, int L, int C,
+                  float scale, cudaStream_t s);
+int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cudaStream_t s);
+int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long long k_ld,
+                 const void* vT16, const float* v_bias, float* S, void* P, void* O16, int N, int L, int C,
+                 float scale, cudaStream_t s);
+
+}  // namespace sfv
+
+struct SfvEncoder {
+  int prec = 0, fmt = 0, chunk = 8;
+  sfv::DeviceBlob blob;
+  sfv::ConvW conv_in, ds[3], q, k, v, qk, proj, conv_out;
+  sfv::ResW down[4][2], mid1, mid2;
+  sfv::NormW attn_norm, norm_out;
+};
+
+struct SfvRbvae {
+  int in_channels = 0, in_h = 0, in_w = 0, channels = 0, layers = 0, L = 0;
+  int fh = 0, fw = 0;                 // feature map after the three stride-2 convs
+  sfv::DeviceBlob blob;
+  sfv::ConvW c0, c1, c2;
+  float* fc_w = nullptr;              // [L][fh*fw*channels], permuted to NHWC flatten order
+  float* fc_b = nullptr;
+  float *w_ih = nullptr, *w_hh = nullptr, *lstm_b = nullptr;   // [layers][4L][L], [layers][4L]
+};
+
+namespace sfv {
+int encoder_build(SfvEncoder* e, const SfvTensor* t, int n);
+size_t encoder_workspace(const SfvEncoder* e, int B, int H, int W);
+int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, int W, float* params,
+                    float* logvar, float* stdv, float* var, void* ws, size_t ws_bytes, float* const* taps,
+                    cudaStream_t s);
+}

@@ -1,0 +1,327 @@
+// norm.cu -- GroupNorm(32, eps=1e-6)+SiLU passes and the other HBM-bound
+// elementwise kernels of the encoder (reference
+// ldm/modules/diffusionmodules/model.py:33-39, distributions.py:24-37).
+//
+// All activations are NHWC so a thread owns 4 consecutive channels of one pixel
+// (16 B fp32 / 8 B 16-bit vector access, coalesced across the warp) and those 4
+// channels always fall in one group (C/32 is 4, 8 or 16).
+// Statistics: fp32 per-thread partial sums -> fp64 shared/global atomics, so the
+// E[x^2]-E[x]^2 subtraction happens in double.
+#include "common.cuh"
+
+namespace sfv {
+namespace {
+
+constexpr int kPixPerBlock = 512;
+
+template <bool IS16>
+__device__ __forceinline__ void load4(const void* base, long long idx, int fmt, float v[4]) {
+  if (IS16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + idx);
+    v[0] = f16_to_32((uint16_t)(u.x & 0xFFFF), fmt); v[1] = f16_to_32((uint16_t)(u.x >> 16), fmt);
+    v[2] = f16_to_32((uint16_t)(u.y & 0xFFFF), fmt); v[3] = f16_to_32((uint16_t)(u.y >> 16), fmt);
+  } else {
+    const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+}
+
+// grid (ceil(HW / kPixPerBlock), N); block 256.  VEC = 4 channels per thread.
+template <bool IS16>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* x, int fmt, long long HW, int C,
+                                                       int G, double* stats) {
+  __shared__ double sh[64][2];
+  const int n = blockIdx.y;
+  const int tpp = C >> 2;                 // threads per pixel
+  const int rows = 256 / tpp;             // pixels per pass (tpp in {8..64} for C<=256; C=512 -> 2)
+  const int tc = threadIdx.x % tpp;
+  const int tr = threadIdx.x / tpp;
+  const int cpg = C / G;
+  const int g = (tc * 4) / cpg;
+  if (threadIdx.x < 2 * G) (&sh[0][0])[threadIdx.x] = 0.0;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * kPixPerBlock;
+  const long long p1 = min(p0 + (long long)kPixPerBlock, HW);
+  float s = 0.f, ss = 0.f;
+  if (tr < rows) {
+    for (long long p = p0 + tr; p < p1; p += rows) {
+      float v[4];
+      load4<IS16>(x, ((long long)n * HW + p) * C + tc * 4, fmt, v);
+      s += (v[0] + v[1]) + (v[2] + v[3]);
+      ss += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+    }
+    atomicAdd(&sh[g][0], (double)s);
+    atomicAdd(&sh[g][1], (double)ss);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * G)
+    atomicAdd(&stats[(long long)n * G * 2 + threadIdx.x], (&sh[0][0])[threadIdx.x]);
+}
+
+// scalar fallback for channel counts whose groups are not multiples of 4 (op tests only)
+__global__ void gn_stats_scalar_kernel(const float* x, long long HW, int C, int G, double* stats) {
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G;
+  double s = 0, ss = 0;
+  for (long long i = threadIdx.x; i < HW * cpg; i += blockDim.x) {
+    const long long p = i / cpg; const int c = g * cpg + (int)(i % cpg);
+    const float v = x[((long long)n * HW + p) * C + c];
+    s += v; ss += (double)v * v;
+  }
+  atomicAdd(&stats[((long long)n * G + g) * 2], s);
+  atomicAdd(&stats[((long long)n * G + g) * 2 + 1], ss);
+}
+
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// grid (ceil(HW / kPixPerBlock), N); block 256
+template <bool IN16, bool OUT16>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* x, const double* stats,
+                                                       const float* gamma, const float* beta, void* y,
+                                                       int fmt, long long HW, int C, int G, float eps,
+                                                       int do_silu) {
+  __shared__ float sh_mean[64], sh_rstd[64];
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    const double cnt = (double)HW * cpg;
+    const double m = stats[((long long)n * G + threadIdx.x) * 2] / cnt;
+    double var = stats[((long long)n * G + threadIdx.x) * 2 + 1] / cnt - m * m;
+    if (var < 0) var = 0;
+    sh_mean[threadIdx.x] = (float)m;
+    sh_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int tpp = C >> 2;
+  const int rows = 256 / tpp;
+  const int tc = threadIdx.x % tpp;
+  const int tr = threadIdx.x / tpp;
+  if (tr >= rows) return;
+  const int g = (tc * 4) / cpg;
+  const float mean = sh_mean[g], rstd = sh_rstd[g];
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + tc * 4);
+  const float4 be = *reinterpret_cast<const float4*>(beta + tc * 4);
+  const float sc[4] = {ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd};
+  const float sf[4] = {be.x - mean * sc[0], be.y - mean * sc[1], be.z - mean * sc[2], be.w - mean * sc[3]};
+  const long long p0 = (long long)blockIdx.x * kPixPerBlock;
+  const long long p1 = min(p0 + (long long)kPixPerBlock, HW);
+  for (long long p = p0 + tr; p < p1; p += rows) {
+    const long long idx = ((long long)n * HW + p) * C + tc * 4;
+    float v[4];
+    load4<IN16>(x, idx, fmt, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = fmaf(v[j], sc[j], sf[j]);
+      v[j] = do_silu ? silu(t) : t;
+    }
+    if (OUT16) {
+      uint2 u; u.x = pack2_16(v[0], v[1], fmt); u.y = pack2_16(v[2], v[3], fmt);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + idx) = u;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+__global__ void gn_apply_scalar_kernel(const float* x, const double* stats, const float* gamma,
+                                       const float* beta, float* y, long long HW, int C, int G,
+                                       float eps, int do_silu, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long n = i / ((long long)HW * C);
+  const int cpg = C / G, g = c / cpg;
+  const double cnt = (double)HW * cpg;
+  const double m = stats[(n * G + g) * 2] / cnt;
+  double var = stats[(n * G + g) * 2 + 1] / cnt - m * m;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float t = (x[i] - (float)m) * rstd * gamma[c] + beta[c];
+  y[i] = do_silu ? silu(t) : t;
+}
+
+__global__ void f32_to_16_kernel(const float* x, uint16_t* y, long long n, int fmt) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 f = *reinterpret_cast<const float4*>(x + i);
+    uint2 u; u.x = pack2_16(f.x, f.y, fmt); u.y = pack2_16(f.z, f.w, fmt);
+    *reinterpret_cast<uint2*>(y + i) = u;
+  } else {
+    for (long long j = i; j < n; ++j) y[j] = f32_to_16(x[j], fmt);
+  }
+}
+
+__global__ void f16_to_32_kernel(const uint16_t* x, float* y, long long n, int fmt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = f16_to_32(x[i], fmt);
+}
+
+// one block per row; cols up to 16384 (mid-block attention at 1024^2)
+template <bool OUT16>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, void* y, int fmt, int cols) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* r = x + (long long)blockIdx.x * cols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 f = *reinterpret_cast<const float4*>(r + c);
+    mx = fmaxf(mx, fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 f = *reinterpret_cast<const float4*>(r + c);
+    sum += (expf(f.x - mx) + expf(f.y - mx)) + (expf(f.z - mx) + expf(f.w - mx));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    bcast = 1.f / s;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 f = *reinterpret_cast<const float4*>(r + c);
+    const float a = expf(f.x - mx) * inv, b = expf(f.y - mx) * inv, cc = expf(f.z - mx) * inv,
+                d = expf(f.w - mx) * inv;
+    const long long o = (long long)blockIdx.x * cols + c;
+    if (OUT16) {
+      uint2 u; u.x = pack2_16(a, b, fmt); u.y = pack2_16(cc, d, fmt);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + o) = u;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o) = make_float4(a, b, cc, d);
+    }
+  }
+}
+
+// DiagonalGaussian head (distributions.py:24-31): moments NHWC [N,HW,8] ->
+//   parameters NCHW [N,8,HW] (raw; mean = channels 0..3), logvar = clamp(ch 4..7, -30, 20),
+//   std = exp(0.5 logvar), var = exp(logvar)   (each NCHW [N,4,HW]; std/var optional)
+__global__ void head_kernel(const float* mom, float* params, float* logvar, float* stdv, float* var, int HW,
+                            long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (n, p)
+  if (i >= total) return;
+  const long long n = i / HW; const int p = (int)(i - n * HW);
+  const float4 a = *reinterpret_cast<const float4*>(mom + i * 8);
+  const float4 b = *reinterpret_cast<const float4*>(mom + i * 8 + 4);
+  const float m[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) params[(n * 8 + c) * HW + p] = m[c];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float lv = fminf(fmaxf(m[4 + c], -30.f), 20.f);
+    const long long o = (n * 4 + c) * HW + p;
+    logvar[o] = lv;
+    if (stdv) stdv[o] = expf(0.5f * lv);
+    if (var) var[o] = expf(lv);
+  }
+}
+
+__global__ void sample_kernel(const float* mean, const float* logvar, const float* noise, float scale,
+                              float* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = mean[i];
+  if (noise) v += expf(0.5f * logvar[i]) * noise[i];
+  out[i] = scale * v;
+}
+
+}  // namespace
+
+int launch_zero(void* p, size_t bytes, cudaStream_t s) {
+  SFV_CUDA(cudaMemsetAsync(p, 0, bytes, s));
+  return 0;
+}
+
+int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int C, int G, double* stats,
+                    cudaStream_t s) {
+  SFV_CHECK(G >= 1 && C % G == 0, "group_norm: bad C=%d G=%d", C, G);
+  SFV_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * G, s));
+  const int cpg = C / G;
+  if (cpg % 4 == 0 && C % 4 == 0 && 256 % (C / 4) == 0 && C <= 1024 && G <= 32) {
+    dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), N);
+    if (x_is16) gn_stats_kernel<true><<<grid, 256, 0, s>>>(x, fmt, HW, C, G, stats);
+    else gn_stats_kernel<false><<<grid, 256, 0, s>>>(x, fmt, HW, C, G, stats);
+  } else {
+    SFV_CHECK(!x_is16, "group_norm: scalar path is fp32 only");
+    gn_stats_scalar_kernel<<<dim3(G, N), 256, 0, s>>>((const float*)x, HW, C, G, stats);
+  }
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma, const float* beta,
+                    void* y, int y_is16, int fmt, int N, long long HW, int C, int G, float eps, int silu,
+                    cudaStream_t s) {
+  const int cpg = C / G;
+  if (cpg % 4 == 0 && C % 4 == 0 && 256 % (C / 4) == 0 && C <= 1024 && G <= 32) {
+    dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), N);
+    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
+    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
+    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
+    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
+  } else {
+    SFV_CHECK(!x_is16 && !y_is16, "group_norm: scalar path is fp32 only");
+    const long long total = (long long)N * HW * C;
+    gn_apply_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        (const float*)x, stats, gamma, beta, (float*)y, HW, C, G, eps, silu, total);
+  }
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t s) {
+  const long long nt = (n + 3) / 4;
+  f32_to_16_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(x, (uint16_t*)y, n, fmt);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s) {
+  f16_to_32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint16_t*)x, y, n, fmt);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,
+                        cudaStream_t s) {
+  SFV_CHECK(cols % 4 == 0, "softmax: cols %% 4 != 0");
+  SFV_CHECK(rows < (1ll << 31), "softmax: too many rows");
+  if (y_is16) softmax_rows_kernel<true><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
+  else softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_head(const float* mom, float* params, float* logvar, float* stdv, float* var, int N, int HW,
+                cudaStream_t s) {
+  const long long total = (long long)N * HW;
+  head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(mom, params, logvar, stdv, var, HW, total);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+int launch_sample(const float* mean, const float* logvar, const float* noise, float scale, float* out,
+                  long long n, cudaStream_t s) {
+  sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mean, logvar, noise, scale, out, n);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace sfv

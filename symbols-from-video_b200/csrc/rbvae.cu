@@ -1,0 +1,131 @@
+// rbvae.cu -- RBVAE encoder-half handle (percep: 256 channels / 4 LSTM layers,
+// contrastive: 64 / 2).  Reference: models/percep_RBVAE/percep_RBVAE_model.py:46-68,
+// 94-107,172-191; models/contrastive_RBVAE/contrastive_RBVAE_model.py:45-67,93-106,171-190.
+//
+// All arithmetic is fp32 on the CUDA-core implicit GEMM: the binary code is the
+// sign of a small LSTM state, so this part is kept at full precision (0.04 % of
+// the pipeline FLOPs).
+#include "common.cuh"
+#include "encoder.h"
+#include <string.h>
+
+namespace sfv {
+
+static const SfvTensor* find_t(const SfvTensor* t, int n, const std::string& name) {
+  for (int i = 0; i < n; ++i)
+    if (t[i].name && name == t[i].name) return &t[i];
+  return nullptr;
+}
+
+int rbvae_build(SfvRbvae* r, const SfvTensor* t, int n) {
+  const SfvTensor* w0 = find_t(t, n, "encoder_cnn.conv.0.weight");
+  const SfvTensor* fcw = find_t(t, n, "encoder_cnn.fc.weight");
+  const SfvTensor* fcb = find_t(t, n, "encoder_cnn.fc.bias");
+  if (!w0 || !fcw || !fcb) return fail(SFV_ERR_MISSING_KEY, "rbvae: missing encoder_cnn.conv.0 / fc tensors");
+  r->channels = (int)w0->shape[0];
+  if (w0->shape[1] != r->in_channels)
+    return fail(SFV_ERR_MISSING_KEY, "rbvae: conv.0 expects %lld input channels, got %d",
+                (long long)w0->shape[1], r->in_channels);
+  r->L = (int)fcw->shape[0];
+  int h = r->in_h, w = r->in_w;
+  for (int i = 0; i < 3; ++i) { h = (h + 2 - 3) / 2 + 1; w = (w + 2 - 3) / 2 + 1; }
+  r->fh = h; r->fw = w;
+  const long long K = (long long)r->channels * h * w;
+  if (fcw->shape[1] != K)
+    return fail(SFV_ERR_MISSING_KEY, "rbvae: fc.in_features %lld does not match %d*%d*%d for a %dx%d input",
+                (long long)fcw->shape[1], r->channels, h, w, r->in_h, r->in_w);
+  const char* names[3] = {"encoder_cnn.conv.0", "encoder_cnn.conv.3", "encoder_cnn.conv.6"};
+  ConvW* cw[3] = {&r->c0, &r->c1, &r->c2};
+  int cin = r->in_channels;
+  for (int i = 0; i < 3; ++i) {
+    const SfvTensor* ww = find_t(t, n, std::string(names[i]) + ".weight");
+    const SfvTensor* bb = find_t(t, n, std::string(names[i]) + ".bias");
+    if (!ww || !bb || ww->shape[0] != r->channels || ww->shape[1] != cin || ww->shape[2] != 3)
+      return fail(SFV_ERR_MISSING_KEY, "rbvae: missing/mis-shaped %s", names[i]);
+    SFV_TRY(make_conv_from_host(r->blob, ww->host_data, bb->host_data, r->channels, cin, 3, FMT_BF16, false, cw[i]));
+    cin = r->channels;
+  }
+  {  // fc weight: reference flatten order is (C,H,W) (nn.Flatten on NCHW); ours is NHWC
+    std::vector<float> p((size_t)r->L * K);
+    const int C = r->channels, HW = h * w;
+    for (int l = 0; l < r->L; ++l)
+      for (int c = 0; c < C; ++c)
+        for (int q = 0; q < HW; ++q)
+          p[(size_t)l * K + (size_t)q * C + c] = fcw->host_data[(size_t)l * K + (size_t)c * HW + q];
+    SFV_TRY(r->blob.upload(p.data(), p.size() * 4, (void**)&r->fc_w));
+    SFV_TRY(r->blob.upload(fcb->host_data, (size_t)r->L * 4, (void**)&r->fc_b));
+  }
+  int layers = 0;
+  while (find_t(t, n, "encoder_rnn.lstm.weight_ih_l" + std::to_string(layers))) ++layers;
+  if (layers < 1) return fail(SFV_ERR_MISSING_KEY, "rbvae: no encoder_rnn.lstm.weight_ih_l0");
+  r->layers = layers;
+  const int L = r->L;
+  std::vector<float> wi((size_t)layers * 4 * L * L), wh((size_t)layers * 4 * L * L), bs((size_t)layers * 4 * L);
+  for (int l = 0; l < layers; ++l) {
+    const std::string sfx = "_l" + std::to_string(l);
+    const SfvTensor* a = find_t(t, n, "encoder_rnn.lstm.weight_ih" + sfx);
+    const SfvTensor* b = find_t(t, n, "encoder_rnn.lstm.weight_hh" + sfx);
+    const SfvTensor* c = find_t(t, n, "encoder_rnn.lstm.bias_ih" + sfx);
+    const SfvTensor* d = find_t(t, n, "encoder_rnn.lstm.bias_hh" + sfx);
+    if (!a || !b || !c || !d || a->shape[0] != 4 * L || a->shape[1] != L || b->shape[0] != 4 * L || b->shape[1] != L)
+      return fail(SFV_ERR_MISSING_KEY, "rbvae: missing/mis-shaped LSTM layer %d (hidden must equal latent_dim %d)", l, L);
+    memcpy(&wi[(size_t)l * 4 * L * L], a->host_data, (size_t)4 * L * L * 4);
+    memcpy(&wh[(size_t)l * 4 * L * L], b->host_data, (size_t)4 * L * L * 4);
+    for (int j = 0; j < 4 * L; ++j) bs[(size_t)l * 4 * L + j] = c->host_data[j] + d->host_data[j];
+  }
+  SFV_TRY(r->blob.upload(wi.data(), wi.size() * 4, (void**)&r->w_ih));
+  SFV_TRY(r->blob.upload(wh.data(), wh.size() * 4, (void**)&r->w_hh));
+  SFV_TRY(r->blob.upload(bs.data(), bs.size() * 4, (void**)&r->lstm_b));
+  return 0;
+}
+
+static void rb_dims(const SfvRbvae* r, int h[4], int w[4]) {
+  h[0] = r->in_h; w[0] = r->in_w;
+  for (int i = 1; i < 4; ++i) { h[i] = (h[i - 1] - 1) / 2 + 1; w[i] = (w[i - 1] - 1) / 2 + 1; }
+}
+
+size_t rbvae_workspace(const SfvRbvae* r, int N) {
+  int h[4], w[4];
+  rb_dims(r, h, w);
+  Arena ar(nullptr, 0);
+  ar.take((size_t)N * h[1] * w[1] * r->channels * 4);
+  ar.take((size_t)N * h[2] * w[2] * r->channels * 4);
+  ar.take((size_t)N * r->L * 4 * 2);
+  return ar.off + 1024;
+}
+
+int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, const float* u, float noise_ratio,
+                 float temperature, int hard, float* h_out, float* z_out, uint32_t* codes, void* ws,
+                 size_t ws_bytes, cudaStream_t s) {
+  const int N = B * T;
+  SFV_CHECK(B >= 1 && T >= 1, "rbvae: empty batch");
+  SFV_CHECK(noise_ratio == 0.f || u != nullptr, "rbvae: noise_ratio != 0 needs the uniform draws U");
+  SFV_CHECK(temperature > 0.f, "rbvae: temperature must be > 0");
+  SFV_CHECK(ws && ws_bytes >= rbvae_workspace(r, N), "rbvae: workspace too small");
+  int h[4], w[4];
+  rb_dims(r, h, w);
+  Arena ar(ws, ws_bytes);
+  float* a1 = (float*)ar.take((size_t)N * h[1] * w[1] * r->channels * 4);
+  float* a2 = (float*)ar.take((size_t)N * h[2] * w[2] * r->channels * 4);
+  float* logits = (float*)ar.take((size_t)N * r->L * 4);
+  float* hbuf = (float*)ar.take((size_t)N * r->L * 4);
+  // frames may exceed the grid.z limit of the GEMM kernel -> slices of 32768
+  for (int n0 = 0; n0 < N; n0 += 32768) {
+    const int nn = (N - n0) < 32768 ? (N - n0) : 32768;
+    const float* xi = x + (size_t)n0 * r->in_channels * h[0] * w[0];
+    float* a1i = a1 + (size_t)n0 * h[1] * w[1] * r->channels;
+    float* a2i = a2 + (size_t)n0 * h[2] * w[2] * r->channels;
+    // conv(s2,p1)+ReLU, conv(s2,p1)+ReLU, conv(s2,p1)   (dropout is identity in eval)
+    SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));
+    SFV_TRY(conv_f32(r->c1, a1i, SRC_NHWC_F32, nn, h[1], w[1], 2, 1, 1, nullptr, a2i, 1, 1.f, s));
+    // third conv output reuses a1 (dead after conv 2)
+    SFV_TRY(conv_f32(r->c2, a2i, SRC_NHWC_F32, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, 0, 1.f, s));
+    SFV_TRY(launch_fc(a1i, r->fc_w, r->fc_b, logits + (size_t)n0 * r->L, nn,
+                      (long long)h[3] * w[3] * r->channels, r->L, nullptr, 0, s));
+  }
+  float* hb = h_out ? h_out : hbuf;
+  return launch_lstm_code(logits, B, T, r->L, r->layers, r->w_ih, r->w_hh, r->lstm_b, u, noise_ratio,
+                          temperature, hard, hb, z_out, codes, s);
+}
+
+}  // namespace sfv

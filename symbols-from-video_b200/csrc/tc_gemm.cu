@@ -1,0 +1,523 @@
+// tc_gemm.cu -- tcgen05 / TMEM / TMA implicit-GEMM for sm_100a.
+//
+// One warp-specialised persistent kernel serves every dense contraction of the
+// hot path:
+//   D[128 pixels x BLOCK_N] += sum over taps, 64-wide K chunks  A_tap[128 x 64] * B[BLOCK_N x 64]^T
+// * A tiles are fetched by TMA from the NHWC 16-bit activation tensor as a
+//   (64 channels x BW x BH) box whose origin is shifted by the filter tap, so
+//   im2col never exists in memory; out-of-bounds box elements (the zero padding
+//   of the convolution, partial tiles, K tails) are zero-filled by the TMA unit.
+//   Stride-2 convolutions use a 5-D view (c + parity_x*C, x/2, parity_y, y/2, n)
+//   of the same tensor, so they need no element strides and no padded copy
+//   (reference: Downsample.forward pads (0,1,0,1), model.py:72-79).
+// * B tiles (weights, or K / V^T for attention) are K-major rows, 128B-swizzled.
+// * tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) accumulates into TMEM;
+//   two accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// * Epilogue warps read TMEM with tcgen05.ld and apply alpha, bias, residual,
+//   ReLU, then write fp32 and/or 16-bit NHWC rows (and optional GroupNorm
+//   partial sums for the consumer's normalisation).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
+// allocator, warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace sfv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // 64 x 16-bit = 128 B = one swizzle row
+constexpr int kThreads = 192;
+constexpr unsigned long long kWatchdogCycles = 4000000000ull;  // ~2 s
+
+struct TcParams {
+  int dim_x, dim_y, dim_n;
+  int ntaps, kchunks;
+  int tap_o[9][5];
+  int tap_k[9];
+  int b_batched;
+  int BW_log2, BW, BH;
+  int tiles_x, tiles_y, n_tiles_m, n_tiles_n, n_tiles;
+  int Wo, Ho, Cout;
+  float alpha;
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  void* out_16;
+  int fmt;
+  long long ldo;
+  int relu;
+  double* gn_stats; int gn_group_log2; int gn_groups;
+  int* err;                            // device watchdog flag
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a pipeline bug must surface as an error code, not as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                          int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  unsigned long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((spin & 255u) == 255u) {
+      if (*abort_flag) return false;
+      if (clock64() - t0 > kWatchdogCycles) {
+        *abort_flag = 1;
+        atomicCAS(err, 0, code);
+        return false;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; kind::f16 covers fp16 and bf16 operands.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread retire.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, 128-byte swizzle, 8-row atoms 1024 B apart
+// (bit layout: cute::UMMA::SmemDescriptor; version=1 for sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate,
+// A/B format fmt (0 = f16, 1 = bf16), both K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+  static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms must start on 1024-byte boundaries
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;
+  uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * C::kStages + 4);
+  volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);
+    }
+    *abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int k_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        const int m_tile = tile / p.n_tiles_n;
+        const int tx = m_tile % p.tiles_x;
+        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+        const int img = m_tile / (p.tiles_x * p.tiles_y);
+        int base[5] = {0, 0, 0, 0, 0};
+        if (p.dim_x >= 0) base[p.dim_x] += tx * p.BW;
+        if (p.dim_y >= 0) base[p.dim_y] += ty * p.BH;
+        if (p.dim_n >= 0) base[p.dim_n] += img;
+        for (int tap = 0; tap < p.ntaps && ok; ++tap) {
+          const int c1 = base[1] + p.tap_o[tap][1], c2 = base[2] + p.tap_o[tap][2];
+          const int c3 = base[3] + p.tap_o[tap][3], c4 = base[4] + p.tap_o[tap][4];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
+            if (!ok) break;
+            const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_arrive_expect_tx(fb, C::kStageBytes);
+            tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+            tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
+                        p.b_batched ? img : 0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.fmt, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+        ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, abort_flag, p.err, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int it = 0; it < k_iters; ++it) {
+          ok = mbar_wait(smem_u32(&full_bar[stage]), phase, abort_flag, p.err, 3);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                     (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when MMAs retire
+          if (it == k_iters - 1) umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int yy = row >> p.BW_log2;
+    const int xx = row & (p.BW - 1);
+    int acc = 0; uint32_t acc_phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int img = m_tile / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.BW + xx, y = ty * p.BH + yy;
+      const bool row_ok = (x < p.Wo) && (y < p.Ho);
+      const long long row_off = (((long long)img * p.Ho + y) * p.Wo + x) * p.ldo;
+      ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, abort_flag, p.err, 4);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += C::kChunk) {
+        uint32_t v[C::kChunk];
+        if constexpr (C::kChunk == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N + c0;
+        if (row_ok && col0 < p.Cout) {
+          float f[C::kChunk];
+#pragma unroll
+          for (int j = 0; j < C::kChunk; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4) {
+              if (col0 + j < p.Cout) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.residual) {
+            const float* r = p.residual + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4) {
+              if (col0 + j < p.Cout) {
+                const float4 b = *reinterpret_cast<const float4*>(r + j);
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4)
+              if (col0 + j < p.Cout)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+          if (p.out_16) {
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 8) {
+              if (col0 + j + 4 < p.Cout) {
+                uint4 u;
+                u.x = pack2_16(f[j], f[j + 1], p.fmt);     u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                u.z = pack2_16(f[j + 4], f[j + 5], p.fmt); u.w = pack2_16(f[j + 6], f[j + 7], p.fmt);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              } else if (col0 + j < p.Cout) {
+                uint2 u;
+                u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                *reinterpret_cast<uint2*>(o + j) = u;
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int* g_err_flag = nullptr;
+int g_num_sms = 0;
+
+int tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SFV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(SFV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  int dev = 0;
+  SFV_CUDA(cudaGetDevice(&dev));
+  SFV_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  SFV_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
+  SFV_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (((uintptr_t)ptr & 15) != 0) return fail(SFV_ERR_INVALID, "TMA base not 16B aligned");
+  for (int i = 1; i < rank; ++i)
+    if (strides_bytes[i] % 16 != 0)
+      return fail(SFV_ERR_INVALID, "TMA stride %d = %llu not a multiple of 16 B", i,
+                  (unsigned long long)strides_bytes[i]);
+  CUresult r = g_encode(m, fmt == FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                        (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes + 1, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SFV_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  return 0;
+}
+
+template <int BLOCK_N>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t s) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  tc_gemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
+  SFV_TRY(tc_init());
+  SFV_CHECK(a.BW * a.BH == kBlockM && (a.BW & (a.BW - 1)) == 0, "tc_gemm: bad tile %dx%d", a.BW, a.BH);
+  SFV_CHECK(a.ntaps >= 1 && a.ntaps <= 9 && a.kchunks >= 1, "tc_gemm: bad taps/kchunks");
+  SFV_CHECK(a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0");
+  SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[5], strides[5]; cuuint32_t box[5];
+    for (int i = 0; i < 5; ++i) {
+      dims[i] = i < a.a_rank ? a.a_dims[i] : 1;
+      strides[i] = i < a.a_rank ? a.a_strides[i] : (i > 0 ? strides[i - 1] * dims[i - 1] : 2);
+      box[i] = i < a.a_rank ? a.a_box[i] : 1;
+    }
+    strides[0] = 2;
+    SFV_TRY(encode_map(&ma, a.fmt, 5, a.a, dims, strides, box));
+  }
+  {
+    cuuint64_t dims[3] = {a.b_k, a.b_rows, a.b_batched ? (cuuint64_t)a.Nimg : 1};
+    cuuint64_t strides[3] = {2, a.b_row_stride, a.b_batched ? a.b_batch_stride : a.b_row_stride * a.b_rows};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)a.block_n, 1};
+    SFV_TRY(encode_map(&mb, a.fmt, 3, a.b, dims, strides, box));
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.dim_x = a.dim_x; p.dim_y = a.dim_y; p.dim_n = a.dim_n;
+  p.ntaps = a.ntaps; p.kchunks = a.kchunks;
+  for (int t = 0; t < a.ntaps; ++t) {
+    for (int i = 0; i < 5; ++i) p.tap_o[t][i] = a.taps[t].o[i];
+    p.tap_k[t] = a.tap_k[t];
+  }
+  p.b_batched = a.b_batched;
+  p.BW = a.BW; p.BH = a.BH; p.BW_log2 = 0;
+  while ((1 << p.BW_log2) < a.BW) ++p.BW_log2;
+  p.tiles_x = ceil_div(a.Wo, a.BW); p.tiles_y = ceil_div(a.Ho, a.BH);
+  p.n_tiles_m = p.tiles_x * p.tiles_y * a.Nimg;
+  p.n_tiles_n = ceil_div(a.Cout, a.block_n);
+  p.n_tiles = p.n_tiles_m * p.n_tiles_n;
+  p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout;
+  p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
+  p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
+  p.gn_stats = a.gn_stats; p.err = g_err_flag;
+  switch (a.block_n) {
+    case 256: return launch_cfg<256>(ma, mb, p, s);
+    case 128: return launch_cfg<128>(ma, mb, p, s);
+    case 64: return launch_cfg<64>(ma, mb, p, s);
+    case 32: return launch_cfg<32>(ma, mb, p, s);
+    case 16: return launch_cfg<16>(ma, mb, p, s);
+    default: return fail(SFV_ERR_INVALID, "tc_gemm: unsupported block_n %d", a.block_n);
+  }
+}
+
+int tc_check_device_error(cudaStream_t s) {
+  if (!g_err_flag) return 0;
+  int h = 0;
+  SFV_CUDA(cudaMemcpyAsync(&h, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SFV_CUDA(cudaStreamSynchronize(s));
+  if (h != 0) {
+    cudaMemsetAsync(g_err_flag, 0, sizeof(int), s);
+    return fail(SFV_ERR_DEVICE, "tcgen05 pipeline watchdog tripped (role code %d)", h);
+  }
+  return 0;
+}
+
+}  // namespace sfv

@@ -1,0 +1,182 @@
+"""Drop-in host mirror of the reference's RBVAE *encoder half*.
+
+* percep      -- models/percep_RBVAE/percep_RBVAE_model.py:125-191
+                 (256-channel convs, 4-layer LSTM, fc hard-wired to 256*11*20)
+* contrastive -- models/contrastive_RBVAE/contrastive_RBVAE_model.py:124-190
+                 (64-channel convs, 2-layer LSTM, fc hard-wired to 64*32*32)
+
+``Seq2SeqBinaryVAE(in_channels, out_channels, latent_dim, hidden_dim)`` keeps
+the reference constructor; ``kind`` / ``input_hw`` are the extra knobs that let
+the fc layer follow the latent shape (the reference fails on anything but its
+native 88x160 / 256x256 input).  State-dict key names are the
+reference's, so ``load_state_dict(torch.load(...)['model_state_dict'])`` works
+unchanged (decoder keys are accepted and ignored).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_KINDS = {"percep": dict(channels=256, layers=4, input_hw=(88, 160)),
+          "contrastive": dict(channels=64, layers=2, input_hw=(256, 256))}
+
+
+def _down3(n):
+    for _ in range(3):
+        n = (n - 1) // 2 + 1
+    return n
+
+
+class _ConvStack(nn.Module):
+    def __init__(self, cin, ch, latent_dim, fin):
+        super().__init__()
+        self.conv = nn.Module()
+        for idx, ci in ((0, cin), (3, ch), (6, ch)):     # Sequential indices of the three Conv2d
+            leaf = nn.Module()
+            leaf.weight = nn.Parameter(torch.zeros(ch, ci, 3, 3), requires_grad=False)
+            leaf.bias = nn.Parameter(torch.zeros(ch), requires_grad=False)
+            self.conv.add_module(str(idx), leaf)
+        self.fc = nn.Module()
+        self.fc.weight = nn.Parameter(torch.zeros(latent_dim, fin), requires_grad=False)
+        self.fc.bias = nn.Parameter(torch.zeros(latent_dim), requires_grad=False)
+
+
+class _Lstm(nn.Module):
+    def __init__(self, L, layers):
+        super().__init__()
+        self.lstm = nn.Module()
+        for l in range(layers):
+            for n, shape in (("weight_ih", (4 * L, L)), ("weight_hh", (4 * L, L)),
+                             ("bias_ih", (4 * L,)), ("bias_hh", (4 * L,))):
+                self.lstm.register_parameter(f"{n}_l{l}", nn.Parameter(torch.zeros(shape), requires_grad=False))
+
+
+class Seq2SeqBinaryVAE(nn.Module):
+    def __init__(self, in_channels=3, out_channels=3, latent_dim=32, hidden_dim=32, kind=None, input_hw=None):
+        super().__init__()
+        if hidden_dim != latent_dim:
+            # the reference ignores hidden_dim too: EncoderRNN(latent_dim, hidden_dim=latent_dim) (:139)
+            hidden_dim = latent_dim
+        if kind is None:
+            kind = "percep" if in_channels == 4 else "contrastive"
+        if kind not in _KINDS:
+            raise ValueError(f"kind must be one of {sorted(_KINDS)}")
+        cfg = _KINDS[kind]
+        self.kind = kind
+        self.latent_dim = latent_dim
+        self.in_channels = in_channels
+        self.channels = cfg["channels"]
+        self.input_hw = tuple(input_hw) if input_hw is not None else cfg["input_hw"]
+        fin = self.channels * _down3(self.input_hw[0]) * _down3(self.input_hw[1])
+        self.encoder_cnn = _ConvStack(in_channels, self.channels, latent_dim, fin)
+        self.encoder_rnn = _Lstm(latent_dim, cfg["layers"])
+        self._handles = {}
+        self._ws = _lib.Workspace()
+
+    # -- weights -------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        own = set(self.state_dict().keys())
+        sd = {k: v for k, v in state_dict.items() if k in own}
+        missing = own - set(sd)
+        if strict and missing:
+            raise RuntimeError(f"missing keys: {sorted(missing)}")
+        fcw = sd.get("encoder_cnn.fc.weight")
+        if fcw is not None and tuple(fcw.shape) != tuple(self.encoder_cnn.fc.weight.shape):
+            if fcw.shape[0] != self.latent_dim:
+                raise RuntimeError(f"fc.weight has latent_dim {fcw.shape[0]}, model has {self.latent_dim}")
+            self.encoder_cnn.fc.weight = nn.Parameter(torch.zeros_like(fcw), requires_grad=False)
+        out = super().load_state_dict(sd, strict=False, **kw)
+        self._release()
+        return out
+
+    def _release(self):
+        for h in self._handles.values():
+            _lib.lib().sfv_rbvae_destroy(h)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _native(self, H, W):
+        key = (H, W)
+        if key not in self._handles:
+            fin = self.channels * _down3(H) * _down3(W)
+            have = self.encoder_cnn.fc.weight.shape[1]
+            if fin != have:
+                # same failure the reference raises from nn.Linear on a mismatching flatten
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied: conv features {fin} for a "
+                                   f"{H}x{W} input vs fc.in_features {have}")
+            table, n, keep = _lib.make_tensor_table(self.state_dict())
+            h = C.c_void_p()
+            _lib.check(_lib.lib().sfv_rbvae_create(table, n, self.in_channels, H, W, C.byref(h)))
+            self._handles[key] = h
+        return self._handles[key]
+
+    # -- the hot path --------------------------------------------------------
+    @torch.no_grad()
+    def _encode(self, x, temperature, hard, noise_ratio, U=None, in_scale=1.0, want_codes=False):
+        _lib.require_cuda(x, "Seq2SeqBinaryVAE input")
+        if x.dim() != 5:
+            raise ValueError(f"expected [B,T,C,H,W], got {tuple(x.shape)}")
+        B, T, Cc, H, W = x.shape
+        if Cc != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} channels, got {Cc}")
+        L = self.latent_dim
+        h = self._native(H, W)
+        x = x.to(torch.float32).contiguous()
+        dev = x.device
+        if U is None and noise_ratio != 0:
+            # same global-RNG CPU draw as binary_concrete_logits (percep_RBVAE_model.py:33)
+            U = torch.rand(B * T, L)
+        if U is not None:
+            U = U.to(device=dev, dtype=torch.float32).reshape(B * T, L).contiguous()
+        h_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)
+        z_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)
+        codes = torch.empty(B * T, (L + 31) // 32, dtype=torch.int32, device=dev) if want_codes else None
+        nbytes = C.c_size_t()
+        lib = _lib.lib()
+        _lib.check(lib.sfv_rbvae_workspace_bytes(h, B * T, C.byref(nbytes)))
+        ws = self._ws.get(nbytes.value, dev)
+        _lib.check(lib.sfv_rbvae_encode(h, _lib.ptr(x), B, T, float(in_scale), _lib.ptr(U), float(noise_ratio),
+                                        float(temperature), int(bool(hard)), _lib.ptr(h_seq), _lib.ptr(z_seq),
+                                        _lib.ptr(codes), _lib.ptr(ws), nbytes.value, _lib.stream_ptr()))
+        return z_seq, h_seq, codes
+
+    def encode(self, x, temperature=0.5, hard=False, noise_ratio=0.1, U=None):
+        """percep_RBVAE_model.py:172-191: x [B,T,C,H,W] -> z_seq [B,T,L]."""
+        return self._encode(x, temperature, hard, noise_ratio, U)[0]
+
+    def encode_codes(self, x, temperature=0.5, noise_ratio=0.0, U=None, in_scale=1.0):
+        """hard code, bit-packed: (codes uint32-as-int32 [B*T, ceil(L/32)], h_seq [B,T,L])."""
+        _, h_seq, codes = self._encode(x, temperature, True, noise_ratio, U, in_scale, want_codes=True)
+        return codes, h_seq
+
+    def forward(self, x, temperature=1.0, hard=False, noise_ratio=0.1, U=None):
+        """percep_RBVAE_model.py:143-170, encoder half: returns (x_recon, h_seq, z_seq)
+        with x_recon = None -- decoder_rnn / ConvDecoder belong to training."""
+        z_seq, h_seq, _ = self._encode(x, temperature, hard, noise_ratio, U)
+        return None, h_seq, z_seq
+
+
+def unpack_codes(codes: torch.Tensor, L: int) -> torch.Tensor:
+    """uint32 words [N, ceil(L/32)] -> float {0,1} [N, L] (bit j of word w = latent 32w+j)."""
+    c = codes.to(torch.int64) & 0xFFFFFFFF
+    bits = (c.unsqueeze(-1) >> torch.arange(32, device=codes.device)) & 1
+    return bits.reshape(codes.shape[0], -1)[:, :L].to(torch.float32)
+
+
+def hamming_matrix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Pairwise Hamming distance of packed codes (embedding_hamming_distance.py:53-87) on the device."""
+    _lib.require_cuda(a, "codes")
+    a = a.contiguous(); b = b.contiguous()
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.int32, device=a.device)
+    _lib.check(_lib.lib().sfv_hamming(_lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0], a.shape[1],
+                                      _lib.ptr(out), _lib.stream_ptr()))
+    return out
