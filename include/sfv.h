@@ -182,6 +182,15 @@ int sfv_op_group_norm(const float* x_nhwc, const float* gamma, const float* beta
 int sfv_op_attention(const float* q, const float* k, const float* v, float* out,
                      int32_t N, int32_t L, int32_t C, float scale, int32_t precision, void* stream);
 
+/* Per-kernel-class device timing for the roofline report (bench.py): while enabled
+ * every launch of a class is bracketed by CUDA events on its own stream.
+ * category: 0 tcgen05 GEMM/conv (work = algorithmic FLOPs), 1 CUDA-core igemm (FLOPs),
+ * 2 GroupNorm statistics, 3 GroupNorm apply, 4 softmax (work = algorithmic bytes), 5 other.
+ * sfv_profile_enable(on) resets the counters; sfv_profile_read synchronises the
+ * recorded events and returns the accumulated milliseconds, work and launch count. */
+int sfv_profile_enable(int32_t on);
+int sfv_profile_read(int32_t category, double* ms, double* work, int64_t* launches);
+
 /* Number of kernel launches issued by this library since load (bench evidence). */
 int64_t sfv_launch_count(void);
 

@@ -1,0 +1,109 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.make_golden
+The reference has no tests or fixtures of its own for this path, so
+these vectors -- outputs of the reference's own classes on seeded inputs and
+seeded random-init weights (no checkpoint exists offline) -- are what
+pins the oracle (tests/test_oracle_golden.py) and, through it, the CUDA path.
+Weights are regenerated from the seed by oracle.kl_f8.init_state_dict /
+oracle.rbvae.init_state_dict, so only inputs' seeds and outputs are stored.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import frames, kl_f8, rbvae, ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def encoder_case(name, seed, shape, frame_seed, smooth):
+    sd = kl_f8.init_state_dict(seed)
+    m = ref_shim.autoencoder_kl(sd)
+    B, H, W = shape
+    u8 = frames.synthetic_frames(B, H, W, seed=frame_seed, smooth=smooth)
+    x = frames.normalise_u8(u8)
+    with torch.no_grad():
+        post = m.encode(x)
+        enc_out = m.encoder(x)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), weight_seed=seed, frame_seed=frame_seed,
+                        smooth=smooth, shape=np.array(shape), mean=post.mean.numpy(),
+                        logvar=post.logvar.numpy(), std=post.std.numpy(), var=post.var.numpy(),
+                        parameters=post.parameters.numpy(), encoder_out_sum=float(enc_out.double().sum()))
+    print(name, "mean std", float(post.mean.std()), "logvar range", float(post.logvar.min()), float(post.logvar.max()))
+
+
+def rbvae_case(name, kind, cin, ch, layers, L, hw, seed, T):
+    fh = hw[0]
+    for _ in range(3):
+        fh = (fh - 1) // 2 + 1
+    fw = hw[1]
+    for _ in range(3):
+        fw = (fw - 1) // 2 + 1
+    sd = rbvae.init_state_dict(cin, L, (fh, fw), channels=ch, num_layers=layers, seed=seed)
+    m = ref_shim.rbvae(kind, cin, L, sd, feat_hw=(fh, fw))
+    g = torch.Generator().manual_seed(seed + 100)
+    B = 3
+    x = torch.randn(B, T, cin, *hw, generator=g) * (0.18215 * 4 if kind == "percep" else 1.0)
+    if kind != "percep":
+        x = torch.rand(B, T, cin, *hw, generator=g)
+    with torch.no_grad():
+        z0 = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.0)
+        # h_seq: the reference only exposes it through forward(), whose decoder half is hard-wired to the
+        # native shape; recompute it from the reference's own sub-modules exactly as encode() does (:176-186)
+        Bq, Tq = x.shape[:2]
+        logits = m.encoder_cnn(x.reshape(Bq * Tq, cin, *hw)).reshape(Bq, Tq, L)
+        h_seq, _ = m.encoder_rnn(logits)
+        torch.manual_seed(777)
+        z_noise = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.3)
+        torch.manual_seed(777)
+        U = torch.rand(Bq * Tq, L)       # the draw binary_concrete_logits made (percep_RBVAE_model.py:33)
+        torch.manual_seed(778)
+        z_soft = m.encode(x, temperature=0.7, hard=False, noise_ratio=0.1)
+        torch.manual_seed(778)
+        U_soft = torch.rand(Bq * Tq, L)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, cin=cin, ch=ch, layers=layers, L=L,
+                        hw=np.array(hw), seed=seed, T=T, x=x.numpy(), logits=logits.numpy(), h=h_seq.numpy(),
+                        z_hard=z0.numpy(), z_noise=z_noise.numpy(), U=U.numpy(), z_soft=z_soft.numpy(),
+                        U_soft=U_soft.numpy())
+    print(name, "min|h|", float(h_seq.abs().min()), "max|h|", float(h_seq.abs().max()))
+
+
+def resize_case():
+    """PIL LANCZOS on the first chinchess frame (768x432 -> 1280x720 -> 1280x704), subsampled."""
+    import cv2
+    from PIL import Image
+    cap = cv2.VideoCapture(os.path.join(ref_shim.REF_ROOT, "videos/chinchess_gettyimages-148739276-640_adpp.mp4"))
+    ok, fr = cap.read()
+    fr = cv2.cvtColor(fr, cv2.COLOR_BGR2RGB)
+    _, u8 = frames.load_img_pil(Image.fromarray(fr))
+    rng = np.random.default_rng(5)
+    small = rng.integers(0, 256, (45, 80, 3), dtype=np.uint8)
+    small_up = np.array(Image.fromarray(small).resize((128, 72), resample=Image.LANCZOS))
+    small_dn = np.array(Image.fromarray(small).resize((32, 24), resample=Image.LANCZOS))
+    np.savez_compressed(os.path.join(OUT, "resize_pil.npz"), frame0=fr, frame0_1280x704_rows=u8[::16],
+                        frame0_checksum=int(u8.astype(np.int64).sum()), small=small, small_up=small_up,
+                        small_dn=small_dn)
+    print("resize_pil checksum", int(u8.astype(np.int64).sum()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    encoder_case("kl_f8_seed0_2x64x96_white", 0, (2, 64, 96), 1234, False)
+    encoder_case("kl_f8_seed1_1x128x128_smooth", 1, (1, 128, 128), 1234, True)
+    encoder_case("kl_f8_seed0_2x256x256_white", 0, (2, 256, 256), 1234, False)      # BASELINE config 1 shape
+    rbvae_case("rbvae_percep_L25_32x32_T1", "percep", 4, 256, 4, 25, (32, 32), 1, 1)
+    rbvae_case("rbvae_percep_L25_64x64_T1", "percep", 4, 256, 4, 25, (64, 64), 2, 1)
+    rbvae_case("rbvae_percep_L100_88x160_T1", "percep", 4, 256, 4, 100, (88, 160), 3, 1)   # reference-native shape
+    rbvae_case("rbvae_percep_L50_32x32_T4", "percep", 4, 256, 4, 50, (32, 32), 4, 4)
+    rbvae_case("rbvae_contrastive_L25_256x256_T1", "contrastive", 3, 64, 2, 25, (256, 256), 5, 1)
+    resize_case()
+
+
+if __name__ == "__main__":
+    main()

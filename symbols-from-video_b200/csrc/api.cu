@@ -19,6 +19,34 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- profiler ----
+bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static double g_prof_ms[PROF_NUM], g_prof_work[PROF_NUM];
+static long long g_prof_n[PROF_NUM];
+static cudaEvent_t ev_get() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int cat, double work, cudaStream_t s) {
+  ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cat = cat; r.work = work;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t s) { cudaEventRecord(g_prof.back().b, s); }
+static void prof_collect() {
+  for (ProfRec& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    g_prof_ms[r.cat] += ms; g_prof_work[r.cat] += r.work; g_prof_n[r.cat] += 1;
+    g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b);
+  }
+  g_prof.clear();
+}
+
 int rbvae_build(SfvRbvae* r, const SfvTensor* t, int n);
 size_t rbvae_workspace(const SfvRbvae* r, int N);
 int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, const float* u, float noise_ratio,
@@ -50,6 +78,21 @@ const char* sfv_version(void) { return "sfv-b200 0.1 (sm_100a)"; }
 const char* sfv_last_error(void) { return g_last_error.c_str(); }
 int sfv_device_ok(void) { return require_device() == 0 ? 1 : 0; }
 int64_t sfv_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sfv_profile_enable(int32_t on) {
+  prof_collect();
+  for (int i = 0; i < PROF_NUM; ++i) { g_prof_ms[i] = 0; g_prof_work[i] = 0; g_prof_n[i] = 0; }
+  g_prof_on = on != 0;
+  return 0;
+}
+int sfv_profile_read(int32_t category, double* ms, double* work, int64_t* launches) {
+  if (category < 0 || category >= PROF_NUM) return fail(SFV_ERR_INVALID, "profile_read: bad category");
+  prof_collect();
+  if (ms) *ms = g_prof_ms[category];
+  if (work) *work = g_prof_work[category];
+  if (launches) *launches = g_prof_n[category];
+  return 0;
+}
 
 int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t precision, SfvEncoder** out) {
   if (!out || !tensors) return fail(SFV_ERR_INVALID, "encoder_create: null argument");

@@ -48,6 +48,18 @@ int fail(int code, const char* fmt, ...);
                        cudaGetErrorString(_e));                                            \
   } while (0)
 
+// ---- optional per-kernel-class timing (bench.py roofline): CUDA events on the launching stream ----
+enum : int { PROF_TC_GEMM = 0, PROF_IGEMM = 1, PROF_GN_STATS = 2, PROF_GN_APPLY = 3, PROF_SOFTMAX = 4,
+             PROF_OTHER = 5, PROF_NUM = 6 };
+extern bool g_prof_on;
+void prof_begin(int cat, double work, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(int cat, double work, cudaStream_t st) : s(st), on(g_prof_on) { if (on) prof_begin(cat, work, s); }
+  ~ProfScope() { if (on) prof_end(s); }
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -145,6 +145,7 @@ int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s) {
   const int M = a.Ho * a.Wo;
   dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN), a.N);
   SFV_CHECK(grid.y <= 65535, "igemm: Cout too large");
+  ProfScope prof(PROF_IGEMM, 2.0 * M * (double)a.N * a.Cout * a.ksize * a.ksize * a.Cin, s);
   igemm_f32_kernel<<<grid, 256, 0, s>>>(a);
   SFV_LAUNCH_OK();
   return 0;

@@ -254,6 +254,7 @@ int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int
   SFV_CHECK(G >= 1 && C % G == 0, "group_norm: bad C=%d G=%d", C, G);
   SFV_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * G, s));
   const int cpg = C / G;
+  ProfScope prof(PROF_GN_STATS, (double)N * HW * C * (x_is16 ? 2 : 4), s);
   if (cpg % 4 == 0 && C % 4 == 0 && 256 % (C / 4) == 0 && C <= 1024 && G <= 32) {
     dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), N);
     if (x_is16) gn_stats_kernel<true><<<grid, 256, 0, s>>>(x, fmt, HW, C, G, stats);
@@ -270,6 +271,7 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
                     void* y, int y_is16, int fmt, int N, long long HW, int C, int G, float eps, int silu,
                     cudaStream_t s) {
   const int cpg = C / G;
+  ProfScope prof(PROF_GN_APPLY, (double)N * HW * C * ((x_is16 ? 2 : 4) + (y_is16 ? 2 : 4)), s);
   if (cpg % 4 == 0 && C % 4 == 0 && 256 % (C / 4) == 0 && C <= 1024 && G <= 32) {
     dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), N);
     if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
@@ -303,6 +305,7 @@ int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long 
                         cudaStream_t s) {
   SFV_CHECK(cols % 4 == 0, "softmax: cols %% 4 != 0");
   SFV_CHECK(rows < (1ll << 31), "softmax: too many rows");
+  ProfScope prof(PROF_SOFTMAX, (double)rows * cols * (4 + (y_is16 ? 2 : 4)), s);
   if (y_is16) softmax_rows_kernel<true><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
   else softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
   SFV_LAUNCH_OK();

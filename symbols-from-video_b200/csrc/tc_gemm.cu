@@ -39,7 +39,7 @@ struct TcParams {
   int b_batched;
   int BW_log2, BW, BH;
   int tiles_x, tiles_y, n_tiles_m, n_tiles_n, n_tiles;
-  int Wo, Ho, Cout;
+  int Wo, Ho, Cout, n_img;
   float alpha;
   const float* bias;
   const float* residual;
@@ -449,6 +449,9 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
     attr_set = true;
   }
   int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
+  const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
+  ProfScope prof(PROF_TC_GEMM, flops, s);
   tc_gemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
   SFV_LAUNCH_OK();
   return 0;
@@ -494,7 +497,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_tiles_m = p.tiles_x * p.tiles_y * a.Nimg;
   p.n_tiles_n = ceil_div(a.Cout, a.block_n);
   p.n_tiles = p.n_tiles_m * p.n_tiles_n;
-  p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout;
+  p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
   p.gn_stats = a.gn_stats; p.err = g_err_flag;

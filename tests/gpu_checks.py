@@ -1,0 +1,327 @@
+"""GPU parity checks shared by tests/test_gpu_parity.py (pytest -m gpu) and
+tools/gpu_diag.py (one subprocess per check, results to gpurun_out/diag.json).
+
+Every check drives the product through its public Python mirror, i.e. through
+the C ABI of libsfv.so, and compares with the CPU oracle on the same seeded
+inputs.  Tolerances (stated per check):
+  fp32 check mode : latent mean/logvar rel-L2 <= 1e-4               (north star)
+  fp16 operands   : latent mean rel-L2 <= 1e-2                        (north star gate)
+  bf16 operands   : latent mean rel-L2 <= max(1e-2, 1.25 x numerics-model floor);
+                    the floor itself (bf16 operand rounding with everything else
+                    exact) is 0.8-1.4e-2 on random-init weights, see oracle/numerics_model.py
+  codes           : bit-exact wherever the oracle's |h + noise| >= 1e-3; flips inside
+                    the band are counted and reported
+  integer work    : bit-exact (resize, bit-packing, Hamming)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+import sfv_b200  # noqa: E402
+from oracle import frames, kl_f8, numerics_model, rbvae as orb  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).detach().double().cpu(); b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def r16(t, prec):
+    return t.to(torch.bfloat16 if prec == "bf16" else torch.float16).float()
+
+
+# ------------------------------------------------------------------ single ops
+def check_conv(prec, N, H, W, Cin, Cout, ks=3, stride=1, pad=(1, 1), residual=False, relu=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    Ho = (H + pad[0] + pad[1] - ks) // stride + 1
+    Wo = (W + pad[0] + pad[1] - ks) // stride + 1
+    res = torch.randn(N, Cout, Ho, Wo, generator=g) if residual else None
+    xe, we = (x, w) if prec == "fp32" else (r16(x, prec), r16(w, prec))
+    ref = F.conv2d(F.pad(xe, (pad[0], pad[1], pad[0], pad[1])), we, b, stride=stride)
+    if residual:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    y = sfv_b200.ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV), w, b, stride=stride, pad=pad,
+                                 residual=None if res is None else res.permute(0, 2, 3, 1).contiguous().to(DEV),
+                                 relu=relu, precision=prec)
+    torch.cuda.synchronize()
+    y = y.permute(0, 3, 1, 2).cpu()
+    err = rel_l2(y, ref)
+    mx = float((y - ref).abs().max())
+    out = dict(rel_l2=err, max_abs=mx, shape=[N, H, W, Cin, Cout, ks, stride, list(pad)], prec=prec)
+    # operands are rounded identically on both sides, products are exact in fp32: only summation order differs
+    assert err < 2e-5, out
+    return out
+
+
+CONV_SHAPES = [
+    # (N, H, W, Cin, Cout, ks, stride, pad, residual)    -- small cases per tile geometry
+    (1, 1, 128, 64, 16, 1, 1, (0, 0), False),     # one tile, one k-chunk, N=16
+    (2, 4, 128, 128, 128, 1, 1, (0, 0), True),    # 1x1, multi-tile, residual
+    (2, 8, 128, 64, 64, 3, 1, (1, 1), False),     # 3x3, 128x1 tiles, halo rows/cols via TMA OOB fill
+    (2, 8, 64, 128, 256, 3, 1, (1, 1), True),     # 64x2 tiles, BLOCK_N 256
+    (1, 12, 32, 128, 128, 3, 1, (1, 1), False),   # 32x4 tiles
+    (1, 5, 40, 64, 32, 3, 1, (1, 1), False),      # ragged: partial tiles in x and y
+    (2, 16, 64, 128, 128, 3, 2, (0, 1), False),   # Downsample: pad right/bottom only
+    (2, 16, 32, 256, 256, 3, 2, (1, 1), False),   # RBVAE style stride 2 pad 1
+    (1, 8, 8, 512, 8, 3, 1, (1, 1), False),       # head: Cout 8 padded to 16
+    (3, 8, 16, 512, 1024, 1, 1, (0, 0), False),   # fused q|k projection shape
+]
+# the distinct (M,N,K) GEMM shapes of SURVEY 2a at 64x64 input resolution
+LAYER_SHAPES_64 = [
+    (1, 64, 64, 128, 128, 3, 1, (1, 1), True), (1, 32, 32, 128, 256, 3, 1, (1, 1), False),
+    (1, 32, 32, 256, 256, 3, 1, (1, 1), True), (1, 16, 16, 256, 512, 3, 1, (1, 1), False),
+    (1, 16, 16, 512, 512, 3, 1, (1, 1), True), (1, 8, 8, 512, 512, 3, 1, (1, 1), True),
+    (1, 64, 64, 128, 128, 3, 2, (0, 1), False), (1, 32, 32, 256, 256, 3, 2, (0, 1), False),
+    (1, 16, 16, 512, 512, 3, 2, (0, 1), False), (1, 32, 32, 128, 256, 1, 1, (0, 0), False),
+    (1, 16, 16, 256, 512, 1, 1, (0, 0), False), (1, 8, 8, 512, 512, 1, 1, (0, 0), True),
+]
+
+
+def check_group_norm(C=128, HW=1000, silu=True, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(2, C, HW, 1, generator=g) * 2 + 0.7
+    ga = torch.randn(C, generator=g); be = torch.randn(C, generator=g)
+    ref = F.group_norm(x, 32, ga, be, 1e-6)
+    if silu:
+        ref = ref * torch.sigmoid(ref)
+    y = sfv_b200.ops.group_norm_nhwc(x[..., 0].permute(0, 2, 1).contiguous().to(DEV), ga, be, 32, 1e-6, silu)
+    y = y.permute(0, 2, 1).cpu()
+    out = dict(rel_l2=rel_l2(y, ref[..., 0]), C=C, HW=HW)
+    assert out["rel_l2"] < 5e-6, out
+    return out
+
+
+def check_attention(prec, N=2, L=256, C=512, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q, k, v = [torch.randn(N, L, C, generator=g) for _ in range(3)]
+    if prec != "fp32":
+        q, k, v = [r16(t, prec) for t in (q, k, v)]
+    s = torch.bmm(q, k.transpose(1, 2)) * C ** -0.5
+    p = F.softmax(s, dim=2)
+    ref = torch.bmm(p if prec == "fp32" else r16(p, prec), v)
+    y = sfv_b200.ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), precision=prec).cpu()
+    out = dict(rel_l2=rel_l2(y, ref), prec=prec, L=L)
+    # 16-bit path: O is stored in 16 bit (half an ulp = 2^-9 / 2^-12 relative)
+    tol = 2e-5 if prec == "fp32" else (6e-3 if prec == "bf16" else 8e-4)
+    assert out["rel_l2"] < tol, out
+    return out
+
+
+def check_resize():
+    g = np.load(os.path.join(GOLDEN, "resize_pil.npz"))
+    fr = torch.from_numpy(g["frame0"])[None].to(DEV)
+    a = sfv_b200.ops.resize_lanczos(fr, 720, 1280)
+    b, f = sfv_b200.ops.resize_lanczos(a, 704, 1280, want_float=True)
+    out = b[0].cpu().numpy()
+    ok1 = np.array_equal(out[::16], g["frame0_1280x704_rows"]) and int(out.astype(np.int64).sum()) == int(g["frame0_checksum"])
+    small = torch.from_numpy(g["small"])[None].to(DEV)
+    ok2 = np.array_equal(sfv_b200.ops.resize_lanczos(small, 72, 128)[0].cpu().numpy(), g["small_up"])
+    ok3 = np.array_equal(sfv_b200.ops.resize_lanczos(small, 24, 32)[0].cpu().numpy(), g["small_dn"])
+    ref_f = frames.normalise_u8(out[None])
+    ok4 = torch.equal(f.cpu(), ref_f)
+    res = dict(video_frame_bit_exact=bool(ok1), up_bit_exact=bool(ok2), down_bit_exact=bool(ok3),
+               normalise_bit_exact=bool(ok4))
+    assert ok1 and ok2 and ok3 and ok4, res
+    return res
+
+
+# ------------------------------------------------------------------ encoder end to end
+def make_vae(prec, seed, chunk=None):
+    sd = kl_f8.init_state_dict(seed)
+    vae = sfv_b200.AutoencoderKL(precision=prec, chunk=chunk)
+    vae.load_state_dict(sd)
+    return vae, sd
+
+
+def check_encoder_golden(prec, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    vae, sd = make_vae(prec, int(g["weight_seed"]))
+    u8 = frames.synthetic_frames(B, H, W, int(g["frame_seed"]), bool(g["smooth"]))
+    x = frames.normalise_u8(u8)
+    post = vae.encode(x.to(DEV))
+    vae.check_async_error()
+    out = dict(prec=prec, case=name, mean=rel_l2(post.mean, g["mean"]), logvar=rel_l2(post.logvar, g["logvar"]),
+               std=rel_l2(post.std, g["std"]), var=rel_l2(post.var, g["var"]))
+    # uint8-fed entry point must agree with the float entry point (same arithmetic, fused gather)
+    post8 = vae.encode_uint8(torch.from_numpy(u8).to(DEV))
+    out["u8_vs_float_maxabs"] = float((post8.parameters - post.parameters).abs().max())
+    if prec == "fp32":
+        assert out["mean"] <= 1e-4 and out["logvar"] <= 1e-4, out
+        assert out["u8_vs_float_maxabs"] == 0.0, out
+    else:
+        floor = numerics_model.encode_moments(x, sd, prec)
+        out["floor_mean"] = rel_l2(floor[:, :4], g["mean"])
+        out["vs_model_mean"] = rel_l2(post.mean, floor[:, :4])
+        out["meets_1e-2"] = bool(out["mean"] <= 1e-2)
+        if prec == "fp16":
+            assert out["mean"] <= 1e-2, out
+        else:
+            assert out["mean"] <= max(1e-2, 1.25 * out["floor_mean"]), out
+    return out
+
+
+def check_encoder_taps(prec, seed=0, B=1, H=64, W=64):
+    """Layer-wise bisection: every block output against the oracle's."""
+    vae, sd = make_vae(prec, seed)
+    x = frames.normalise_u8(frames.synthetic_frames(B, H, W, 99))
+    taps_ref = {}
+    ref = kl_f8.encode(x, sd, taps_ref)
+    post, taps = vae.encode_with_taps(x.to(DEV))
+    vae.check_async_error()
+    out = {}
+    for name, t in taps.items():
+        if name == "moments":
+            r = ref.parameters
+        else:
+            r = taps_ref[name]
+        out[name] = rel_l2(t.permute(0, 3, 1, 2), r)
+    tol = 1e-4 if prec == "fp32" else 3e-2
+    bad = {k: v for k, v in out.items() if not (v <= tol)}
+    assert not bad, dict(prec=prec, bad=bad, all=out)
+    return out
+
+
+def check_chunking_and_batch_independence(prec="fp32"):
+    """Frames are independent: chunked == unchunked, and batch row i == single frame i."""
+    vae, sd = make_vae(prec, 0, chunk=2)
+    x = frames.normalise_u8(frames.synthetic_frames(5, 32, 32, 5)).to(DEV)
+    a = vae.encode(x).parameters
+    vae2, _ = make_vae(prec, 0, chunk=8)
+    b = vae2.encode(x).parameters
+    c = vae2.encode(x[3:4]).parameters
+    out = dict(chunk_maxabs=float((a - b).abs().max()), single_vs_batch=rel_l2(c, b[3:4]))
+    assert out["chunk_maxabs"] < 1e-5 and out["single_vs_batch"] < 1e-5, out
+    return out
+
+
+# ------------------------------------------------------------------ RBVAE
+def rb_from_golden(g):
+    hw = [int(v) for v in g["hw"]]
+    fh, fw = hw
+    for _ in range(3):
+        fh, fw = (fh - 1) // 2 + 1, (fw - 1) // 2 + 1
+    sd = orb.init_state_dict(int(g["cin"]), int(g["L"]), (fh, fw), channels=int(g["ch"]),
+                             num_layers=int(g["layers"]), seed=int(g["seed"]))
+    m = sfv_b200.Seq2SeqBinaryVAE(int(g["cin"]), int(g["cin"]), int(g["L"]), int(g["L"]), kind=str(g["kind"]),
+                                  input_hw=tuple(hw))
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def code_flips(z, z_ref, margin):
+    """(flips outside the |logit|<1e-3 band, flips inside, band size)."""
+    diff = z != z_ref
+    band = np.abs(margin) < 1e-3
+    return int((diff & ~band).sum()), int((diff & band).sum()), int(band.sum())
+
+
+def check_rbvae_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd = rb_from_golden(g)
+    L = int(g["L"])
+    x = torch.from_numpy(g["x"]).to(DEV)
+    z = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.0)
+    _, h, _ = m.forward(x, temperature=0.5, hard=True, noise_ratio=0.0)
+    codes, h2 = m.encode_codes(x)
+    z, h, h2 = z.cpu().numpy(), h.cpu().numpy(), h2.cpu().numpy()
+    out = dict(case=name, h_maxabs=float(np.abs(h - g["h"]).max()))
+    o, i, n = code_flips(z, g["z_hard"], g["h"])
+    out.update(flips_outside=o, flips_inside=i, band=n, bits=int(z.size))
+    assert out["h_maxabs"] < 2e-5, out
+    assert o == 0, out
+    assert np.array_equal(h, h2)
+    # packed code == packed float code, bit layout as oracle.rbvae.pack_codes
+    packed = codes.cpu().numpy().astype(np.int64).astype(np.uint32).reshape(-1, (L + 31) // 32)
+    assert np.array_equal(packed, orb.pack_codes(torch.from_numpy(z).reshape(-1, L))), out
+    assert np.array_equal(sfv_b200.unpack_codes(codes, L).cpu().numpy(), z.reshape(-1, L))
+    # stochastic: same uniform draw as the reference consumed (supplied U)
+    U = torch.from_numpy(g["U"])
+    zn = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.3, U=U).cpu().numpy()
+    noise = orb.logistic_noise(U, 0.3).reshape(g["h"].shape).numpy()
+    o2, i2, n2 = code_flips(zn, g["z_noise"], g["h"] + noise)
+    out.update(noise_flips_outside=o2, noise_flips_inside=i2)
+    assert o2 == 0, out
+    # ... and drawn internally from the global CPU RNG exactly like binary_concrete_logits does
+    torch.manual_seed(777)
+    zn2 = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.3).cpu().numpy()
+    assert np.array_equal(zn, zn2), "global-RNG draw differs from the reference's"
+    zs = m.encode(x, temperature=0.7, hard=False, noise_ratio=0.1, U=torch.from_numpy(g["U_soft"])).cpu().numpy()
+    out["soft_maxabs"] = float(np.abs(zs - g["z_soft"]).max())
+    assert out["soft_maxabs"] < 2e-5, out
+    return out
+
+
+def check_hamming():
+    g = torch.Generator().manual_seed(0)
+    a = torch.randint(-2 ** 31, 2 ** 31 - 1, (37, 4), generator=g, dtype=torch.int64).to(torch.int32)
+    b = torch.randint(-2 ** 31, 2 ** 31 - 1, (21, 4), generator=g, dtype=torch.int64).to(torch.int32)
+    d = sfv_b200.hamming_matrix(a.to(DEV), b.to(DEV)).cpu()
+    ua = sfv_b200.unpack_codes(a, 128); ub = sfv_b200.unpack_codes(b, 128)
+    ref = (ua[:, None, :] != ub[None, :, :]).sum(-1).to(torch.int32)
+    assert torch.equal(d, ref)
+    return dict(ok=True)
+
+
+# ------------------------------------------------------------------ whole pipeline
+def check_pipeline(prec="fp16", B=6, R=64, L=25, seed=0, batch=4):
+    """uint8 frames -> latents -> packed codes through FramePipeline (host buffers, double-buffered
+    upload) against oracle(encoder) -> oracle(rbvae)."""
+    vae, sd = make_vae(prec, seed)
+    lh = R // 8
+    fh = lh
+    for _ in range(3):
+        fh = (fh - 1) // 2 + 1
+    rsd = orb.init_state_dict(4, L, (fh, fh), seed=seed + 1)
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, L, L, input_hw=(lh, lh))
+    rb.load_state_dict(rsd)
+    u8 = frames.synthetic_frames(B, R, R, 4321, smooth=True)
+    pipe = sfv_b200.FramePipeline(vae, rb, batch=batch)
+    res = pipe.encode_host(torch.from_numpy(u8).pin_memory())
+    vae.check_async_error()
+    post = kl_f8.encode(frames.normalise_u8(u8), sd)
+    lat_ref = kl_f8.first_stage_encoding(post, use_mode=True)
+    z_ref, h_ref = orb.encode(lat_ref[:, None], rsd, hard=True, noise_ratio=0.0, return_h=True)
+    z = sfv_b200.unpack_codes(res.codes, L).numpy()
+    o, i, n = code_flips(z, z_ref[:, 0].numpy(), h_ref[:, 0].numpy())
+    out = dict(prec=prec, latent_rel_l2=rel_l2(res.latents, lat_ref), h_maxabs=float((res.h - h_ref[:, 0]).abs().max()),
+               flips_outside=o, flips_inside=i, band=n, bits=int(z.size))
+    tol = 1e-4 if prec == "fp32" else 2e-2
+    assert out["latent_rel_l2"] <= tol, out
+    if prec == "fp32":
+        assert o == 0, out
+    return out
+
+
+def check_full_size_properties(prec="bf16", B=4, R=512):
+    """BASELINE config-2 frame size, where the CPU oracle is too slow: size-independent
+    properties -- batch permutation equivariance, determinism, finite outputs, logvar clamp range."""
+    vae, sd = make_vae(prec, 0)
+    u8 = torch.from_numpy(frames.synthetic_frames(B, R, R, 11, smooth=True)).to(DEV)
+    a = vae.encode_uint8(u8).parameters.clone()
+    b = vae.encode_uint8(u8).parameters.clone()
+    perm = torch.tensor([2, 0, 3, 1], device=DEV)[:B]
+    c = vae.encode_uint8(u8[perm].contiguous()).parameters
+    vae.check_async_error()
+    out = dict(deterministic=bool(torch.equal(a, b)), perm_rel=rel_l2(c, a[perm]), finite=bool(torch.isfinite(a).all()),
+               mean_std=float(a[:, :4].std()))
+    assert out["deterministic"] or rel_l2(a, b) < 1e-6, out
+    assert out["perm_rel"] < 1e-6 and out["finite"], out
+    return out

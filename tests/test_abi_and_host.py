@@ -1,0 +1,183 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sfv.h declares,
+fails loudly without a GPU (no fallback), and the host-side mirror keeps the
+reference's call surface (state-dict keys, signatures, npy format, sharding)."""
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+import sfv_b200
+from oracle import kl_f8, rbvae as orb
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "sfv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = sfv_b200.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"libsfv.so does not export {s}"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(sfv_b200._lib.SIGNATURES) == syms
+    assert b"sm_100a" in lib.sfv_version()
+
+
+def test_library_has_tcgen05_and_tma_sass():
+    out = subprocess.run(["cuobjdump", "-sass", sfv_b200._lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "UTCHMMA" in out.stdout and "UTMALDG" in out.stdout and "LDTM" in out.stdout
+    assert "HMMA.16816" not in out.stdout        # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    assert sfv_b200.lib().sfv_device_ok() == 0
+    vae = sfv_b200.AutoencoderKL()
+    with pytest.raises(sfv_b200.SfvError):
+        vae.encode(torch.zeros(1, 3, 64, 64))           # CPU tensor -> refuse
+    table, n, keep = sfv_b200._lib.make_tensor_table(vae.state_dict())
+    import ctypes as C
+    h = C.c_void_p()
+    st = sfv_b200.lib().sfv_encoder_create(table, n, 1, C.byref(h))
+    assert st == -2 and b"no CPU fallback" in sfv_b200.lib().sfv_last_error()
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25)
+    with pytest.raises(sfv_b200.SfvError):
+        rb.encode(torch.zeros(1, 1, 4, 88, 160))
+
+
+def test_product_never_imports_oracle():
+    code = "import sys, sfv_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    pkg = os.path.join(ROOT, "symbols-from-video_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#include\s+.*oracle)", re.M)
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dp, f)).read()), f
+
+
+def test_autoencoder_state_dict_keys_match_reference_names():
+    vae = sfv_b200.AutoencoderKL(ddconfig=dict(kl_f8.DDCONFIG), lossconfig={"target": "torch.nn.Identity"}, embed_dim=4)
+    ref_sd = kl_f8.init_state_dict(0)
+    own = vae.state_dict()
+    assert set(own) == set(ref_sd)
+    for k in own:
+        assert tuple(own[k].shape) == tuple(ref_sd[k].shape), k
+    # SD checkpoints: prefixed keys + decoder keys, strict=False (get_percep_embeddings.py:34-39)
+    ck = {"first_stage_model." + k: v for k, v in ref_sd.items()}
+    ck["first_stage_model.decoder.conv_in.weight"] = torch.zeros(1)
+    ck["model.diffusion_model.foo"] = torch.zeros(1)
+    vae.load_state_dict(ck, strict=False)
+    assert torch.equal(vae.state_dict()["encoder.conv_in.weight"], ref_sd["encoder.conv_in.weight"])
+    with pytest.raises(ValueError):
+        sfv_b200.AutoencoderKL(ddconfig=dict(kl_f8.DDCONFIG, ch=64))
+
+
+def test_posterior_class_matches_reference_semantics_on_cpu():
+    g = torch.Generator().manual_seed(0)
+    params = torch.randn(2, 8, 4, 4, generator=g) * 20
+    p = sfv_b200.DiagonalGaussianDistribution(params)
+    o = kl_f8.Posterior(params)
+    assert torch.equal(p.mean, o.mean) and torch.equal(p.logvar, o.logvar)
+    assert torch.equal(p.std, o.std) and torch.equal(p.var, o.var)
+    assert p.logvar.max() <= 20 and p.logvar.min() >= -30
+    assert torch.allclose(p.kl(), o.kl())
+    assert p.mode() is p.mean and p.latent_dist is p
+    noise = torch.randn(p.mean.shape, generator=g)
+    assert torch.allclose(p.sample(noise), o.sample(noise))
+    torch.manual_seed(5); a = p.sample()
+    torch.manual_seed(5); b = o.sample()
+    assert torch.equal(a, b)                               # same global-RNG consumption as the reference
+
+
+def test_rbvae_state_dict_keys_and_fc_resize():
+    rb = sfv_b200.Seq2SeqBinaryVAE(in_channels=4, out_channels=4, latent_dim=25, hidden_dim=25)
+    assert rb.encoder_cnn.fc.weight.shape == (25, 256 * 11 * 20)       # reference default, percep_RBVAE_model.py:61
+    ref = orb.init_state_dict(4, 25, (11, 20), seed=0)
+    assert set(ref) == set(rb.state_dict())
+    # a checkpoint also carries decoder keys (percep_RBVAE_train.py:697-702) -> ignored
+    ck = dict(ref); ck["decoder_cnn.fc.weight"] = torch.zeros(3); ck["decoder_rnn.lstm.weight_ih_l0"] = torch.zeros(3)
+    rb.load_state_dict(ck)
+    assert torch.equal(rb.state_dict()["encoder_rnn.lstm.bias_hh_l3"], ref["encoder_rnn.lstm.bias_hh_l3"])
+    # square BASELINE shapes: fc follows the latent shape
+    rb2 = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, input_hw=(64, 64))
+    assert rb2.encoder_cnn.fc.weight.shape == (25, 256 * 8 * 8)
+    rb2.load_state_dict(orb.init_state_dict(4, 25, (4, 4), seed=0))    # adopts the checkpoint's fc shape
+    assert rb2.encoder_cnn.fc.weight.shape == (25, 256 * 4 * 4)
+    c = sfv_b200.Seq2SeqBinaryVAE(in_channels=3, out_channels=3, latent_dim=32, hidden_dim=32)
+    assert c.kind == "contrastive" and c.encoder_cnn.fc.weight.shape == (32, 64 * 32 * 32)
+    assert "encoder_rnn.lstm.weight_ih_l1" in c.state_dict() and "encoder_rnn.lstm.weight_ih_l2" not in c.state_dict()
+
+
+def test_shard_range_partitions_contiguously():
+    for n in (0, 1, 7, 64, 480, 1000):
+        for w in (1, 2, 3, 4, 8):
+            rs = [sfv_b200.shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            for a, b in zip(rs, rs[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sfv_b200.shard_range(10, 2, 2)
+
+
+def test_embedding_store_format(tmp_path):
+    lat = np.random.default_rng(0).standard_normal((3, 4, 8, 8)).astype(np.float32)
+    keys = [f"{i:010d}.jpg" for i in (0, 5, 9)]
+    p = str(tmp_path / "chin_chess_perceps.npy")
+    sfv_b200.save_embeddings_npy(p, keys, lat)
+    d = np.load(p, allow_pickle=True).item()               # the reference's reader, percep_RBVAE_train.py:204
+    assert sorted(d) == keys and d[keys[1]].shape == (1, 4, 8, 8) and d[keys[1]].dtype == np.float32
+    assert np.array_equal(sfv_b200.lookup_embedding(d, 5)[0], lat[1])
+    d2 = {k[:-4]: v for k, v in d.items()}                   # keys without ".jpg" also resolve (:337-350)
+    assert np.array_equal(sfv_b200.lookup_embedding(d2, 9)[0], lat[2])
+    with pytest.raises(KeyError):
+        sfv_b200.lookup_embedding(d, 4)
+
+
+def test_unpack_codes_roundtrip():
+    z = (torch.rand(5, 70, generator=torch.Generator().manual_seed(0)) > 0.5).float()
+    packed = torch.from_numpy(orb.pack_codes(z).astype(np.int64).astype(np.int32))
+    assert torch.equal(sfv_b200.unpack_codes(packed, 70), z)
+
+
+def test_all_gather_ragged_gloo_world2(tmp_path):
+    """N>1 host path: contiguous ranges + ragged all-gather, gloo on CPU, world_size 2."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r})
+        import sfv_b200
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        N = 7
+        lo, hi = sfv_b200.shard_range(N, r, w)
+        full_codes = torch.arange(N * 2, dtype=torch.int32).reshape(N, 2)
+        full_lat = torch.arange(N * 4 * 2 * 2, dtype=torch.float32).reshape(N, 4, 2, 2)
+        counts = [sfv_b200.shard_range(N, i, w)[1] - sfv_b200.shard_range(N, i, w)[0] for i in range(w)]
+        codes = sfv_b200.all_gather_ragged(full_codes[lo:hi].clone(), counts)
+        lat = sfv_b200.all_gather_ragged(full_lat[lo:hi].clone(), counts)
+        assert torch.equal(codes, full_codes) and torch.equal(lat, full_lat), (r, codes)
+        dist.destroy_process_group()
+        print("rank", r, "ok", lo, hi)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

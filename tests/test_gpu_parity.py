@@ -1,0 +1,84 @@
+"""pytest -m gpu: the parity tests proper (CUDA path through the C ABI vs the CPU oracle)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _c():
+    import gpu_checks
+    return gpu_checks
+
+
+@pytest.mark.parametrize("shape", range(10))
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+def test_conv_tile_geometries(prec, shape):
+    c = _c()
+    N, H, W, Cin, Cout, ks, st, pad, res = c.CONV_SHAPES[shape]
+    c.check_conv(prec, N, H, W, Cin, Cout, ks, st, pad, residual=res, seed=shape)
+
+
+@pytest.mark.parametrize("shape", range(12))
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_conv_layer_shapes(prec, shape):
+    c = _c()
+    N, H, W, Cin, Cout, ks, st, pad, res = c.LAYER_SHAPES_64[shape]
+    c.check_conv(prec, N, H, W, Cin, Cout, ks, st, pad, residual=res, seed=100 + shape)
+
+
+def test_conv_small_channels_fp32():
+    c = _c()
+    c.check_conv("fp32", 2, 17, 23, 3, 128, 3, 1, (1, 1))            # conv_in shape class (K = 27)
+    c.check_conv("fp32", 2, 9, 11, 4, 256, 3, 2, (1, 1), relu=True)  # RBVAE conv.0 (odd sizes)
+    c.check_conv("fp32", 1, 11, 20, 64, 64, 3, 2, (1, 1))
+
+
+@pytest.mark.parametrize("C,HW", [(128, 4096), (256, 1000), (512, 77), (64, 333)])
+def test_group_norm(C, HW):
+    _c().check_group_norm(C, HW, silu=True)
+    _c().check_group_norm(C, HW, silu=False, seed=1)
+
+
+@pytest.mark.parametrize("prec,L", [("fp32", 256), ("bf16", 256), ("fp16", 1024), ("bf16", 144)])
+def test_attention(prec, L):
+    _c().check_attention(prec, N=2, L=L)
+
+
+def test_resize_bit_exact_vs_pil_golden():
+    _c().check_resize()
+
+
+@pytest.mark.parametrize("name", ["kl_f8_seed0_2x64x96_white", "kl_f8_seed1_1x128x128_smooth",
+                                  "kl_f8_seed0_2x256x256_white"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_encoder_vs_reference_golden(prec, name):
+    print(_c().check_encoder_golden(prec, name))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_encoder_layerwise(prec):
+    print(_c().check_encoder_taps(prec))
+
+
+def test_chunking_and_batch_independence():
+    _c().check_chunking_and_batch_independence("fp32")
+    _c().check_chunking_and_batch_independence("bf16")
+
+
+@pytest.mark.parametrize("name", ["rbvae_percep_L25_32x32_T1", "rbvae_percep_L25_64x64_T1",
+                                  "rbvae_percep_L100_88x160_T1", "rbvae_percep_L50_32x32_T4",
+                                  "rbvae_contrastive_L25_256x256_T1"])
+def test_rbvae_vs_reference_golden(name):
+    print(_c().check_rbvae_golden(name))
+
+
+def test_hamming():
+    _c().check_hamming()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_pipeline_frames_to_codes(prec):
+    print(_c().check_pipeline(prec))
+
+
+def test_full_size_properties_512():
+    print(_c().check_full_size_properties("bf16", B=4, R=512))
