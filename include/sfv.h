@@ -190,6 +190,8 @@ int sfv_op_attention(const float* q, const float* k, const float* v, float* out,
  * recorded events and returns the accumulated milliseconds, work and launch count. */
 int sfv_profile_enable(int32_t on);
 int sfv_profile_read(int32_t category, double* ms, double* work, int64_t* launches);
+/* Per-launch records since sfv_profile_enable(1): lines "category,ms,work,shape tag". */
+const char* sfv_profile_log(void);
 
 /* Number of kernel launches issued by this library since load (bench evidence). */
 int64_t sfv_launch_count(void);

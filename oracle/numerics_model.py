@@ -31,13 +31,22 @@ def encode_moments(x, sd, fmt="bf16"):
     def conv(a16, name, stride=1, pad=0):
         return F.conv2d(a16, r(sd[name + ".weight"]), sd[name + ".bias"], stride=stride, padding=pad)
 
-    def gn(t, name, silu=True):
-        y = F.group_norm(t, 32, sd[name + ".weight"], sd[name + ".bias"], 1e-6)
+    def gn(t, name, silu=True, stats_from=None):
+        # statistics come from the producer's fp32 values (conv epilogue), the normalised tensor
+        # is what was stored (16-bit for conv1's output)
+        src = t if stats_from is None else stats_from
+        b_, c_ = src.shape[:2]
+        g = src.reshape(b_, 32, -1).double()
+        mean = g.mean(-1); var = (g * g).mean(-1) - mean * mean
+        rstd = (1.0 / torch.sqrt(var + 1e-6)).float().repeat_interleave(c_ // 32, 1)[:, :, None, None]
+        mean = mean.float().repeat_interleave(c_ // 32, 1)[:, :, None, None]
+        sc = sd[name + ".weight"][None, :, None, None] * rstd
+        y = t * sc + (sd[name + ".bias"][None, :, None, None] - mean * sc)
         return r(y * torch.sigmoid(y) if silu else y)
 
     def res(t, n):
-        h = r(conv(gn(t, n + ".norm1"), n + ".conv1", 1, 1))
-        h = conv(gn(h, n + ".norm2"), n + ".conv2", 1, 1)
+        h32 = conv(gn(t, n + ".norm1"), n + ".conv1", 1, 1)
+        h = conv(gn(r(h32), n + ".norm2", stats_from=h32), n + ".conv2", 1, 1)
         if (n + ".nin_shortcut.weight") in sd:
             t = conv(r(t), n + ".nin_shortcut")
         return t + h

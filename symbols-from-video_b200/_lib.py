@@ -45,6 +45,7 @@ SIGNATURES = {
     "sfv_launch_count": (C.c_int64, []),
     "sfv_profile_enable": (C.c_int, [C.c_int32]),
     "sfv_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "sfv_profile_log": (C.c_char_p, []),
     "sfv_encoder_create": (C.c_int, [C.POINTER(SfvTensor), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "sfv_encoder_destroy": (None, [_P]),
     "sfv_encoder_precision": (C.c_int, [_P]),

@@ -21,7 +21,8 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- profiler ----
 bool g_prof_on = false;
-struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct ProfRec { cudaEvent_t a, b; int cat; double work; char tag[96]; };
+static std::string g_prof_log;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_ev_pool;
 static double g_prof_ms[PROF_NUM], g_prof_work[PROF_NUM];
@@ -30,8 +31,9 @@ static cudaEvent_t ev_get() {
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-void prof_begin(int cat, double work, cudaStream_t s) {
+void prof_begin(int cat, double work, cudaStream_t s, const char* tag) {
   ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cat = cat; r.work = work;
+  snprintf(r.tag, sizeof(r.tag), "%s", tag ? tag : "");
   cudaEventRecord(r.a, s);
   g_prof.push_back(r);
 }
@@ -42,6 +44,11 @@ static void prof_collect() {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
     g_prof_ms[r.cat] += ms; g_prof_work[r.cat] += r.work; g_prof_n[r.cat] += 1;
+    if (g_prof_log.size() < (1u << 22)) {
+      char line[192];
+      snprintf(line, sizeof(line), "%d,%.4f,%.6g,%s\n", r.cat, ms, r.work, r.tag);
+      g_prof_log += line;
+    }
     g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b);
   }
   g_prof.clear();
@@ -82,6 +89,7 @@ int64_t sfv_launch_count(void) { return (int64_t)g_launches.load(); }
 int sfv_profile_enable(int32_t on) {
   prof_collect();
   for (int i = 0; i < PROF_NUM; ++i) { g_prof_ms[i] = 0; g_prof_work[i] = 0; g_prof_n[i] = 0; }
+  g_prof_log.clear();
   g_prof_on = on != 0;
   return 0;
 }
@@ -94,6 +102,11 @@ int sfv_profile_read(int32_t category, double* ms, double* work, int64_t* launch
   return 0;
 }
 
+const char* sfv_profile_log(void) {
+  prof_collect();
+  return g_prof_log.c_str();
+}
+
 int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t precision, SfvEncoder** out) {
   if (!out || !tensors) return fail(SFV_ERR_INVALID, "encoder_create: null argument");
   *out = nullptr;
@@ -104,6 +117,7 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
   if (!e) return fail(SFV_ERR_INVALID, "out of host memory");
   e->prec = precision;
   e->fmt = fmt_of_precision(precision);
+  if (const char* v = getenv("SFV_FUSED_STATS")) e->fused_stats = atoi(v) != 0;
   int st = encoder_build(e, tensors, n_tensors);
   if (st != 0) { e->blob.release(); delete e; return st; }
   *out = e;

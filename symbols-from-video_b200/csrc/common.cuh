@@ -52,11 +52,13 @@ int fail(int code, const char* fmt, ...);
 enum : int { PROF_TC_GEMM = 0, PROF_IGEMM = 1, PROF_GN_STATS = 2, PROF_GN_APPLY = 3, PROF_SOFTMAX = 4,
              PROF_OTHER = 5, PROF_NUM = 6 };
 extern bool g_prof_on;
-void prof_begin(int cat, double work, cudaStream_t s);
+void prof_begin(int cat, double work, cudaStream_t s, const char* tag);
 void prof_end(cudaStream_t s);
 struct ProfScope {
   cudaStream_t s; bool on;
-  ProfScope(int cat, double work, cudaStream_t st) : s(st), on(g_prof_on) { if (on) prof_begin(cat, work, s); }
+  ProfScope(int cat, double work, cudaStream_t st, const char* tag = nullptr) : s(st), on(g_prof_on) {
+    if (on) prof_begin(cat, work, s, tag);
+  }
   ~ProfScope() { if (on) prof_end(s); }
 };
 
@@ -121,6 +123,8 @@ struct IgemmArgs {
   int nchw_out;              // write y as NCHW [N,Cout,Ho,Wo] instead
 };
 int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
+int launch_conv_in(const void* x, int src_kind, const float* w, const float* bias, float* y, double* stats,
+                   int N, int H, int W, cudaStream_t s);
 
 // ---- norm / elementwise ------------------------------------------------------
 // stats: double [N][G][2] accumulators (sum, sumsq) -- zeroed by the caller/kernel.
@@ -168,7 +172,7 @@ struct TcGemmArgs {
   // epilogue
   float alpha; const float* bias; const float* residual;
   float* out_f32; void* out_16; int fmt; long long ldo; int relu;
-  double* gn_stats; int gn_group;    // optional fused GroupNorm partial sums
+  double* gn_stats; int gn_cpg;      // optional fused GroupNorm partial sums [Nimg][Cout/gn_cpg][2] (pre-zeroed)
 };
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s);
 int tc_check_device_error(cudaStream_t s);   // sync + read the watchdog flag

@@ -1,0 +1,113 @@
+// conv_in.cu -- Encoder.conv_in (3x3, 3 -> 128, pad 1; model.py:383-387,439) fed
+// straight from the boundary layout: uint8 HWC frames (load_img's /255 and 2x-1
+// fused, get_percep_embeddings.py:67-71) or the reference's fp32 NCHW tensor.
+//
+// K = 27 does not fit UMMA and the layer is write-bound (512 B of fp32 NHWC per
+// pixel against 3456 FMAs), so it runs on CUDA cores: a warp owns one pixel row
+// segment, lane l owns output channels 4l..4l+3 (= GroupNorm group l of
+// down.0.block.0.norm1), its 27x4 weights live in registers, the input patch is
+// staged in shared memory and read as warp broadcasts, and each pixel is written
+// as one coalesced 512-byte row.  The GroupNorm statistics of the output are
+// accumulated on the fly (fp32 per lane, fp64 atomics per block).
+#include "common.cuh"
+
+namespace sfv {
+namespace {
+
+constexpr int TH = 8, TW = 32;
+
+template <int SRC>
+__global__ void __launch_bounds__(256, 1)
+conv_in_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               float* __restrict__ y, double* __restrict__ stats, int H, int W, int tiles_x, int tiles) {
+  __shared__ float patch[TH + 2][TW + 2][3];
+  __shared__ float red[8][32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.y;
+  float wr[27][4];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w + k * 128 + lane * 4));
+    wr[k][0] = t.x; wr[k][1] = t.y; wr[k][2] = t.z; wr[k][3] = t.w;
+  }
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + lane * 4));
+  float s_sum = 0.f, s_sq = 0.f;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * 3; i += 256) {
+      const int c = i % 3;
+      const int cc = (i / 3) % (TW + 2);
+      const int r = i / (3 * (TW + 2));
+      const int iy = y0 + r - 1, ix = x0 + cc - 1;
+      float v = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        if (SRC == SRC_NHWC_U8) {
+          const uint8_t u = reinterpret_cast<const uint8_t*>(x)[(((long long)n * H + iy) * W + ix) * 3 + c];
+          const float f = (float)u / 255.0f;
+          v = 2.f * f - 1.f;
+        } else {
+          v = reinterpret_cast<const float*>(x)[(((long long)n * 3 + c) * H + iy) * W + ix];
+        }
+      }
+      patch[r][cc][c] = v;
+    }
+    __syncthreads();
+    const int oy = y0 + warp;
+    if (oy < H) {
+      float* yrow = y + (((long long)n * H + oy) * W + x0) * 128 + lane * 4;
+#pragma unroll 2
+      for (int px = 0; px < TW; ++px) {
+        if (x0 + px >= W) break;
+        float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float v = patch[warp + r][px + sx][c];
+              const int k = (r * 3 + sx) * 3 + c;
+              a0 = fmaf(v, wr[k][0], a0); a1 = fmaf(v, wr[k][1], a1);
+              a2 = fmaf(v, wr[k][2], a2); a3 = fmaf(v, wr[k][3], a3);
+            }
+        *reinterpret_cast<float4*>(yrow + (long long)px * 128) = make_float4(a0, a1, a2, a3);
+        s_sum += (a0 + a1) + (a2 + a3);
+        s_sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+  }
+  if (stats) {
+    red[warp][lane][0] = s_sum; red[warp][lane][1] = s_sq;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int g = threadIdx.x >> 1, m = threadIdx.x & 1;
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][g][m];
+      atomicAdd(&stats[((long long)n * 32 + g) * 2 + m], (double)t);
+    }
+  }
+}
+
+}  // namespace
+
+// x: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W]; w: fp32 [27][128]; y: fp32 NHWC [N,H,W,128];
+// stats_or_null: fp64 [N][32][2] (pre-zeroed) receives sum / sum of squares per GroupNorm group.
+int launch_conv_in(const void* x, int src_kind, const float* w, const float* bias, float* y, double* stats,
+                   int N, int H, int W, cudaStream_t s) {
+  SFV_CHECK(src_kind == SRC_NHWC_U8 || src_kind == SRC_NCHW_F32, "conv_in: unsupported source layout");
+  SFV_CHECK(N <= 65535, "conv_in: batch too large");
+  const int tiles_x = ceil_div(W, TW), tiles = tiles_x * ceil_div(H, TH);
+  const int gx = tiles < 160 ? tiles : 160;
+  ProfScope prof(PROF_IGEMM, 2.0 * N * (double)H * W * 128 * 27, s);
+  if (src_kind == SRC_NHWC_U8)
+    conv_in_kernel<SRC_NHWC_U8><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles);
+  else
+    conv_in_kernel<SRC_NCHW_F32><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles);
+  SFV_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace sfv

@@ -199,7 +199,8 @@ static int pick_block_n(int cout_pad) {
 
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
 int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
-            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s) {
+            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
+            double* gn_stats) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
@@ -248,6 +249,10 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
   a.block_n = pick_block_n(w.cout_pad);
   a.alpha = 1.f; a.bias = w.bias; a.residual = residual;
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
+  if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
+    SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
+    a.gn_stats = gn_stats; a.gn_cpg = w.Cout / 32;
+  }
   return launch_tc_gemm(a, s);
 }
 
@@ -271,7 +276,7 @@ namespace {
 struct Plan {
   float *xa, *xb;
   void *oa, *ob, *x16, *x16b;
-  double* stats;
+  double* stats; double* stats2;
   float* S; void* P; float* moments;
   int attn_chunk;
 };
@@ -287,6 +292,7 @@ void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
   p->x16 = tc ? ar.take(E0 * osz) : nullptr;        // 16-bit copy of x feeding a downsample; V^T in attention
   p->x16b = tc ? ar.take(E0 / 4 * osz) : nullptr;   // 16-bit copy of a downsample output feeding nin_shortcut
   p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
+  p->stats2 = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   const size_t per_img = L * L * (tc ? 6 : 4);
   size_t na = (size_t)(1536ull << 20) / (per_img ? per_img : 1);
   if (na < 1) na = 1;
@@ -300,36 +306,45 @@ void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
 struct Fwd {
   SfvEncoder* e; cudaStream_t s; bool tc; int fmt; Plan pl; int N;
 
-  int gn(const NormW& nw, const void* in, bool in_is16, long long HW, int silu, void* out) {
-    SFV_TRY(launch_gn_stats(in, in_is16, fmt, N, HW, nw.C, 32, pl.stats, s));
-    return launch_gn_apply(in, in_is16, pl.stats, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s);
+  // GroupNorm(32, eps 1e-6)(+SiLU).  `ready`: statistics already accumulated by the producing
+  // kernel's epilogue (tensor-core mode); otherwise a statistics pass runs first (check mode).
+  int gn(const NormW& nw, const void* in, bool in_is16, long long HW, int silu, void* out, const double* ready) {
+    if (!ready) {
+      SFV_TRY(launch_gn_stats(in, in_is16, fmt, N, HW, nw.C, 32, pl.stats, s));
+      ready = pl.stats;
+    }
+    return launch_gn_apply(in, in_is16, ready, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s);
   }
-  // operand-typed input -> fp32 stream and/or operand-typed output
+  // operand-typed input -> fp32 stream and/or operand-typed output (+ fused GN statistics of the output)
   int conv(const ConvW& w, const void* in_op, int H, int W, int stride, const float* residual,
-           float* out_stream, void* out_op) {
+           float* out_stream, void* out_op, double* stats_out) {
     // 3x3 s1: pad 1/1;  1x1: none;  3x3 s2 (Downsample): zero pad right/bottom only (model.py:75-77)
     const int pad_lo = (w.ks == 3 && stride == 1) ? 1 : 0;
     const int pad_hi = (w.ks == 3) ? 1 : 0;
-    if (tc) return conv_tc(w, fmt, in_op, N, H, W, stride, pad_lo, pad_hi, residual, out_stream, out_op, 0, s);
+    if (tc) return conv_tc(w, fmt, in_op, N, H, W, stride, pad_lo, pad_hi, residual, out_stream, out_op, 0, s, stats_out);
     float* y = out_stream ? out_stream : (float*)out_op;
     return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, residual, y, 0, 1.f, s);
   }
+  // statistics buffers: sx holds the stats of the current stream x (written by whichever kernel
+  // produced x), sh those of conv1's output; both null in check mode.
+  double* sx() { return (tc && e->fused_stats) ? pl.stats2 : nullptr; }
+  double* sh() { return (tc && e->fused_stats) ? pl.stats : nullptr; }
 
   // x: fp32 stream (C=Cin), x_op: operand copy of x (needed only when r.has_nin).
   // Writes the block output to `xo` (and its operand copy to pl.x16 if want_copy).
   int resblock(const ResW& r, const float* x, const void* x_op, int H, int W, float* xo, bool want_copy,
                const void** xo_op) {
     const long long HW = (long long)H * W;
-    SFV_TRY(gn(r.n1, x, false, HW, 1, pl.oa));
-    SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob));
-    SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa));
+    SFV_TRY(gn(r.n1, x, false, HW, 1, pl.oa, sx()));
+    SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
+    SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
     const float* res = x;
     if (r.has_nin) {
-      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr));
+      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr, nullptr));
       res = xo;
     }
     void* copy = (tc && want_copy) ? pl.x16 : nullptr;
-    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy));
+    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy, sx()));
     *xo_op = tc ? copy : (const void*)xo;
     return 0;
   }
@@ -338,12 +353,12 @@ struct Fwd {
     const int L = h * w;
     const int C = 512;
     const float scale = 1.0f / sqrtf((float)C);
-    SFV_TRY(gn(e->attn_norm, x, false, L, 0, pl.oa));       // hn (no SiLU)
+    SFV_TRY(gn(e->attn_norm, x, false, L, 0, pl.oa, sx()));       // hn (no SiLU)
     if (tc) {
       SFV_CHECK(L % 8 == 0, "tensor-core attention needs (H/8)*(W/8) %% 8 == 0 (got %d)", L);
       uint16_t* qk = (uint16_t*)pl.ob;                      // [N][L][1024]: q | k
       uint16_t* vT = (uint16_t*)pl.x16;                     // [N][512][L]
-      SFV_TRY(conv_tc(e->qk, fmt, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s));
+      SFV_TRY(conv_tc(e->qk, fmt, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s, nullptr));
       // bias b_v is added after P V (rows of P sum to 1)
       SFV_TRY(vT_tc(e->v, fmt, pl.oa, vT, N, L, s));
       uint16_t* O = (uint16_t*)pl.oa;                       // [N][L][512]  (hn is dead after the two GEMMs above)
@@ -353,7 +368,7 @@ struct Fwd {
                              vT + (size_t)n0 * C * L, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
                              scale, s));
       }
-      SFV_TRY(conv_tc(e->proj, fmt, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s));
+      SFV_TRY(conv_tc(e->proj, fmt, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s, sx()));
     } else {
       float* q = (float*)pl.ob;
       float* k = q + (size_t)N * L * C;
@@ -478,7 +493,8 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     };
     // conv_in straight from the boundary layout (fp32 NCHW or uint8 HWC)
     const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
-    SFV_TRY(conv_f32(e->conv_in, xin, src_kind, N, H, W, 1, 1, 1, nullptr, f.pl.xa, 0, 1.f, s));
+    if (f.sx()) SFV_CUDA(cudaMemsetAsync(f.sx(), 0, sizeof(double) * 2 * 32 * N, s));
+    SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, f.pl.xa, f.sx(), N, H, W, s));
     SFV_TRY(tap(0, f.pl.xa, H, W));
     float* cur = f.pl.xa; float* oth = f.pl.xb;
     const void* cur_op = tc ? nullptr : (const void*)cur;
@@ -494,7 +510,7 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
       if (l != 3) {
         // downsample output feeds down.(l+1).block.0, whose nin_shortcut (levels 1, 2) reads x directly
         const bool want_copy = tc && e->down[l + 1][0].has_nin;
-        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr));
+        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr, f.sx()));
         ch /= 2; cw /= 2;
         std::swap(cur, oth);
         cur_op = tc ? (want_copy ? (const void*)f.pl.x16b : nullptr) : (const void*)cur;
@@ -510,8 +526,8 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     SFV_TRY(f.resblock(e->mid2, cur, nullptr, ch, cw, oth, false, &cur_op));
     std::swap(cur, oth);
     SFV_TRY(tap(14, cur, ch, cw));
-    SFV_TRY(f.gn(e->norm_out, cur, false, L, 1, f.pl.oa));
-    SFV_TRY(f.conv(e->conv_out, f.pl.oa, ch, cw, 1, nullptr, f.pl.moments, nullptr));
+    SFV_TRY(f.gn(e->norm_out, cur, false, L, 1, f.pl.oa, f.sx()));
+    SFV_TRY(f.conv(e->conv_out, f.pl.oa, ch, cw, 1, nullptr, f.pl.moments, nullptr, nullptr));
     SFV_TRY(tap(15, f.pl.moments, ch, cw));
     SFV_TRY(launch_head(f.pl.moments, params + (size_t)b0 * 8 * L, logvar + (size_t)b0 * 4 * L,
                         stdv ? stdv + (size_t)b0 * 4 * L : nullptr, var ? var + (size_t)b0 * 4 * L : nullptr, N,

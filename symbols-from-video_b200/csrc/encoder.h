@@ -22,7 +22,8 @@ struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
 int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
                         int fmt, bool want16, ConvW* out);
 int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
-            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s);
+            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
+            double* gn_stats = nullptr);
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
              int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s);
 int attention_f32(const float* q, const float* k, const float* v, float* O, float* S, int N, int L, int C,
@@ -36,6 +37,7 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
 
 struct SfvEncoder {
   int prec = 0, fmt = 0, chunk = 8;
+  bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
   sfv::DeviceBlob blob;
   sfv::ConvW conv_in, ds[3], q, k, v, qk, proj, conv_out;
   sfv::ResW down[4][2], mid1, mid2;

@@ -74,12 +74,33 @@ __global__ void gn_stats_scalar_kernel(const float* x, long long HW, int C, int 
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
-// grid (ceil(HW / kPixPerBlock), N); block 256
+// GroupNorm apply (+SiLU): y = silu((x - mean_g) * rstd_g * gamma + beta).
+// A thread owns 8 consecutive channels (32 B fp32 / 16 B 16-bit in, 16 B 16-bit out) and
+// walks pixels with a 4-deep unrolled load batch so enough bytes are in flight to cover
+// HBM latency.  grid (pixel slabs, N); block 256.
+template <bool IN16>
+__device__ __forceinline__ void load8(const void* base, long long idx, int fmt, float v[8]) {
+  if (IN16) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = f16_to_32((uint16_t)(w[j] & 0xFFFF), fmt);
+      v[2 * j + 1] = f16_to_32((uint16_t)(w[j] >> 16), fmt);
+    }
+  } else {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
 template <bool IN16, bool OUT16>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const void* x, const double* stats,
-                                                       const float* gamma, const float* beta, void* y,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, void* __restrict__ y,
                                                        int fmt, long long HW, int C, int G, float eps,
-                                                       int do_silu) {
+                                                       int do_silu, int pix_per_block) {
   __shared__ float sh_mean[64], sh_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
@@ -92,33 +113,49 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* x, const doub
     sh_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  const int tpp = C >> 2;
+  const int tpp = C >> 3;                 // threads per pixel
   const int rows = 256 / tpp;
   const int tc = threadIdx.x % tpp;
   const int tr = threadIdx.x / tpp;
-  if (tr >= rows) return;
-  const int g = (tc * 4) / cpg;
-  const float mean = sh_mean[g], rstd = sh_rstd[g];
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + tc * 4);
-  const float4 be = *reinterpret_cast<const float4*>(beta + tc * 4);
-  const float sc[4] = {ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd};
-  const float sf[4] = {be.x - mean * sc[0], be.y - mean * sc[1], be.z - mean * sc[2], be.w - mean * sc[3]};
-  const long long p0 = (long long)blockIdx.x * kPixPerBlock;
-  const long long p1 = min(p0 + (long long)kPixPerBlock, HW);
-  for (long long p = p0 + tr; p < p1; p += rows) {
-    const long long idx = ((long long)n * HW + p) * C + tc * 4;
-    float v[4];
-    load4<IN16>(x, idx, fmt, v);
+  float sc[8], sf[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float t = fmaf(v[j], sc[j], sf[j]);
-      v[j] = do_silu ? silu(t) : t;
+  for (int j = 0; j < 8; ++j) {
+    const int c = tc * 8 + j;
+    const int g = c / cpg;
+    sc[j] = gamma[c] * sh_rstd[g];
+    sf[j] = beta[c] - sh_mean[g] * sc[j];
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(p0 + (long long)pix_per_block, HW);
+  const long long base = (long long)n * HW * C + tc * 8;
+  constexpr int U = 4;
+  for (long long p = p0 + tr; p < p1; p += (long long)rows * U) {
+    float v[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * rows;
+      if (pp < p1) load8<IN16>(x, base + pp * C, fmt, v[u]);
     }
-    if (OUT16) {
-      uint2 u; u.x = pack2_16(v[0], v[1], fmt); u.y = pack2_16(v[2], v[3], fmt);
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + idx) = u;
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * rows;
+      if (pp >= p1) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(v[u][j], sc[j], sf[j]);
+        v[u][j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
+      }
+      const long long idx = base + pp * C;
+      if (OUT16) {
+        uint4 o;
+        o.x = pack2_16(v[u][0], v[u][1], fmt); o.y = pack2_16(v[u][2], v[u][3], fmt);
+        o.z = pack2_16(v[u][4], v[u][5], fmt); o.w = pack2_16(v[u][6], v[u][7], fmt);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + idx) = o;
+      } else {
+        float* o = reinterpret_cast<float*>(y) + idx;
+        *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+      }
     }
   }
 }
@@ -272,12 +309,17 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
                     cudaStream_t s) {
   const int cpg = C / G;
   ProfScope prof(PROF_GN_APPLY, (double)N * HW * C * ((x_is16 ? 2 : 4) + (y_is16 ? 2 : 4)), s);
-  if (cpg % 4 == 0 && C % 4 == 0 && 256 % (C / 4) == 0 && C <= 1024 && G <= 32) {
-    dim3 grid((unsigned)((HW + kPixPerBlock - 1) / kPixPerBlock), N);
-    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
-    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
-    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
-    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu);
+  if (C % 8 == 0 && 256 % (C / 8) == 0 && C <= 2048 && G <= 64 && C % G == 0) {
+    // slabs sized so that the grid is a few waves of 148 SMs x 8 resident blocks
+    long long want = (HW * N + 148 * 16 - 1) / (148 * 16);
+    int ppb = (int)(want < 64 ? 64 : (want > 1024 ? 1024 : want));
+    const int rows = 256 / (C / 8);
+    ppb = (ppb + rows * 4 - 1) / (rows * 4) * (rows * 4);
+    dim3 grid((unsigned)((HW + ppb - 1) / ppb), N);
+    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
   } else {
     SFV_CHECK(!x_is16 && !y_is16, "group_norm: scalar path is fp32 only");
     const long long total = (long long)N * HW * C;
@@ -285,6 +327,7 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
         (const float*)x, stats, gamma, beta, (float*)y, HW, C, G, eps, silu, total);
   }
   SFV_LAUNCH_OK();
+  (void)cpg;
   return 0;
 }
 

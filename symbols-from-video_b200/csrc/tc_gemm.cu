@@ -38,7 +38,7 @@ struct TcParams {
   int tap_k[9];
   int b_batched;
   int BW_log2, BW, BH;
-  int tiles_x, tiles_y, n_tiles_m, n_tiles_n, n_tiles;
+  int tiles_x, tiles_y, n_tiles_m, n_tiles_n, n_tiles, n_units;
   int Wo, Ho, Cout, n_img;
   float alpha;
   const float* bias;
@@ -48,7 +48,8 @@ struct TcParams {
   int fmt;
   long long ldo;
   int relu;
-  double* gn_stats; int gn_group_log2; int gn_groups;
+  double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
+  int epi_mode;
   int* err;                            // device watchdog flag
 };
 
@@ -171,6 +172,72 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants -------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Both CTAs of the pair issue their own loads into their own shared memory; the transaction
+// bytes are reported to the LEADER CTA's barrier (peer bit of the cluster address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_5d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// M = 256 over the CTA pair: each CTA supplies its 128 rows of A and half of B's rows, and
+// receives its 128 accumulator rows in its own TMEM.  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar_local), "r"(cta)
+      : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle, 8-row atoms 1024 B apart
 // (bit layout: cute::UMMA::SmemDescriptor; version=1 for sm_100).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -184,27 +251,82 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate,
 // A/B format fmt (0 = f16, 1 = bf16), both K-major, M = 128, N = n.
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int n) {
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int n, int m) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kBlockM >> 4) << 24);
+         ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_N>
+
+// ---- fused GroupNorm statistics (epilogue) -----------------------------------
+// Each lane holds NV partial sums for its pixel row (sum and sum of squares of NG
+// channel groups).  Recursive halving: at every step a lane keeps one half of its
+// values and adds the partner's copy of that half, so NV values cost NV-1 (+log)
+// shuffles instead of 5*NV; value `idx` ends, fully reduced over the 32 rows, in
+// the lanes whose upper bits spell idx.
+template <int NV>
+__device__ __forceinline__ float halving_reduce(float (&v)[NV], int lane, int& idx) {
+  int base = 0;
+  int off = 16;
+#pragma unroll
+  for (int cnt = NV; cnt > 1; cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+    const int half = cnt >> 1;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    base += up ? half : 0;
+    off >>= 1;
+  }
+  float r = v[0];
+  for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+  idx = base;
+  return r;
+}
+
+// f: this lane's 32 finished output values (columns c0..c0+31 of its pixel row).
+template <int CPG>
+__device__ __forceinline__ void epi_stats_chunk(const float* f, bool valid, int lane, float* acc_w, int group0) {
+  constexpr int NG = 32 / CPG;
+  constexpr int NV = 2 * NG;
+  float v[NV];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float t = valid ? f[g * CPG + j] : 0.f;
+      s += t; q = fmaf(t, t, q);
+    }
+    v[2 * g] = s; v[2 * g + 1] = q;
+  }
+  int idx;
+  const float r = halving_reduce<NV>(v, lane, idx);
+  if ((lane & (32 / NV - 1)) == 0) acc_w[group0 * 2 + idx] += r;   // one owner lane per (group, moment): no race
+}
+
+template <int BLOCK_N, int NCTA>
 struct Cfg {
-  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / NCTA) * kBlockK * 2;      // a CTA pair splits B's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*GN partials*/ + 4 * 32 * 36 * 4 /*epilogue transpose tiles*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, NCTA>;
+  // NCTA == 2: the kernel runs as clusters of two CTAs (one SM pair) that share one
+  // 256-pixel x BLOCK_N tile; rank 0 issues the MMAs for both (tcgen05 cta_group::2).
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / NCTA, unit_step = gridDim.x / NCTA;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -215,6 +337,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
   uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * C::kStages + 4);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
+  float* gn_acc = (float*)((uint8_t*)bars + 256);       // [4 epilogue warps][64 groups][2]
+  float* stage_all = gn_acc + 512;                       // [4 epilogue warps][32 rows][36 words]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -226,14 +350,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4);
+      mbar_init(smem_u32(&tempty_bar[i]), 4 * NCTA);
     }
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
+  for (int i = threadIdx.x; i < 512; i += kThreads) gn_acc[i] = 0.f;
+  if (warp == 1) {
+    if constexpr (NCTA == 2) tmem_alloc_2cta(smem_u32(tmem_ptr), C::kTmemCols);
+    else tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();     // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int k_iters = p.ntaps * p.kchunks;
@@ -243,9 +372,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles_n;
-        const int m_tile = tile / p.n_tiles_n;
+      for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+        const int n_tile = unit % p.n_tiles_n;
+        const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;   // may be a phantom tile (>= n_tiles_m): all OOB -> zeros
         const int tx = m_tile % p.tiles_x;
         const int ty = (m_tile / p.tiles_x) % p.tiles_y;
         const int img = m_tile / (p.tiles_x * p.tiles_y);
@@ -253,6 +382,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.dim_x >= 0) base[p.dim_x] += tx * p.BW;
         if (p.dim_y >= 0) base[p.dim_y] += ty * p.BH;
         if (p.dim_n >= 0) base[p.dim_n] += img;
+        if (p.dim_n < 0 && p.dim_y < 0 && m_tile >= p.n_tiles_m) base[p.dim_x] = 0x3fffffff;   // phantom row block
         for (int tap = 0; tap < p.ntaps && ok; ++tap) {
           const int c1 = base[1] + p.tap_o[tap][1], c2 = base[2] + p.tap_o[tap][2];
           const int c3 = base[3] + p.tap_o[tap][3], c4 = base[4] + p.tap_o[tap][4];
@@ -261,23 +391,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!ok) break;
             const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, C::kStageBytes);
-            tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
-            tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
-                        p.b_batched ? img : 0);
+            if constexpr (NCTA == 2) {
+              // the leader's barrier collects the bytes of both CTAs' loads
+              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kStageBytes);
+              tma_load_5d_2cta(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+              tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK,
+                               n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
+            } else {
+              mbar_arrive_expect_tx(fb, C::kStageBytes);
+              tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+              tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
+                          p.b_batched ? img : 0);
+            }
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.fmt, BLOCK_N);
+    // ===================== MMA issuer (one lane; leader CTA only in pair mode) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(p.fmt, BLOCK_N, kBlockM * NCTA);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+      for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
         ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, abort_flag, p.err, 2);
         if (!ok) break;
         tc_fence_after();
@@ -292,11 +430,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                     (it > 0 || k > 0) ? 1u : 0u);
+            if constexpr (NCTA == 2)
+              umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when MMAs retire
-          if (it == k_iters - 1) umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete
+          if constexpr (NCTA == 2) {
+            umma_commit_2cta(smem_u32(&empty_bar[stage]), 3);             // frees the stage in both CTAs
+            if (it == k_iters - 1) umma_commit_2cta(smem_u32(&tfull_bar[acc]), 3);
+          } else {
+            umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when MMAs retire
+            if (it == k_iters - 1) umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -308,74 +453,223 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = quarter * 32 + lane;
     const int yy = row >> p.BW_log2;
     const int xx = row & (p.BW - 1);
+    float* acc_w = gn_acc + quarter * 128;
+    float* stage_w = stage_all + quarter * (32 * 36);
+    int gn_img = -1, gn_nt = 0;
+    // GroupNorm partials are kept per warp in shared memory across the tiles of one image and
+    // flushed with fp64 global atomics when the (image, n_tile) key changes.
+    auto gn_flush = [&]() {
+      __syncwarp();
+      const int ng2 = 2 * (BLOCK_N / p.gn_cpg);
+      const int g0 = gn_nt * BLOCK_N / p.gn_cpg;
+      for (int t = lane; t < ng2; t += 32) {
+        const float val = acc_w[t];
+        acc_w[t] = 0.f;
+        const int grp = g0 + (t >> 1);
+        if (grp < p.gn_groups)
+          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (t & 1)], (double)val);
+      }
+      __syncwarp();
+    };
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
+    for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+      const int n_tile = unit % p.n_tiles_n;
+      const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
+      const bool tile_ok = m_tile < p.n_tiles_m;
       const int tx = m_tile % p.tiles_x;
       const int ty = (m_tile / p.tiles_x) % p.tiles_y;
       const int img = m_tile / (p.tiles_x * p.tiles_y);
       const int x = tx * p.BW + xx, y = ty * p.BH + yy;
-      const bool row_ok = (x < p.Wo) && (y < p.Ho);
+      const bool row_ok = tile_ok && (x < p.Wo) && (y < p.Ho);
       const long long row_off = (((long long)img * p.Ho + y) * p.Wo + x) * p.ldo;
+      if (p.gn_stats && tile_ok && (img != gn_img || n_tile != gn_nt)) {
+        if (gn_img >= 0) gn_flush();
+        gn_img = img; gn_nt = n_tile;
+      }
       ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, abort_flag, p.err, 4);
       if (!ok) break;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if constexpr (C::kChunk == 32) {
+        // Coalesced epilogue.  TMEM hands each lane one pixel row (32 consecutive channels), but
+        // writing rows straight from registers makes every warp store touch 32 different
+        // 128-byte lines.  Rows are therefore transposed through a per-warp shared-memory
+        // tile (row pitch 36 words: conflict-free for 128-bit accesses): global loads/stores
+        // are issued with 8 lanes per fp32 row (4 lanes per 16-bit row), i.e. whole lines.
+        if (p.epi_mode == 0) {
+          // reference epilogue: every lane writes its own pixel row straight from registers
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += C::kChunk) {
-        uint32_t v[C::kChunk];
-        if constexpr (C::kChunk == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + c0;
-        if (row_ok && col0 < p.Cout) {
-          float f[C::kChunk];
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int col0 = n_tile * BLOCK_N + c0;
+            if (col0 >= p.Cout) break;
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < C::kChunk; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-          if (p.bias) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < C::kChunk; j += 4) {
-              if (col0 + j < p.Cout) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.Cout) {
+                  if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                  }
+                  if (p.residual) {
+                    const float4 b = *reinterpret_cast<const float4*>(p.residual + row_off + col0 + j);
+                    f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                  }
+                  if (p.relu) { f[j] = fmaxf(f[j], 0.f); f[j + 1] = fmaxf(f[j + 1], 0.f); f[j + 2] = fmaxf(f[j + 2], 0.f); f[j + 3] = fmaxf(f[j + 3], 0.f); }
+                  if (p.out_f32)
+                    *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                  if (p.out_16) {
+                    uint2 u; u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0 + j) = u;
+                  }
+                }
+              }
+            }
+            if (p.gn_stats) {
+              if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
+              else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
+              else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
+            }
+          }
+        } else {
+          float* st = stage_w;
+          // rows this lane serves in the transposed patterns
+          long long off32[8]; long long off16[4];
+          unsigned ok32 = 0, ok16 = 0;
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = quarter * 32 + i * 4 + (lane >> 3);
+            const int rx = tx * p.BW + (r & (p.BW - 1)), ry = ty * p.BH + (r >> p.BW_log2);
+            off32[i] = (((long long)img * p.Ho + ry) * p.Wo + rx) * p.ldo;
+            ok32 |= (unsigned)(tile_ok && (rx < p.Wo) && (ry < p.Ho)) << i;
+          }
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = quarter * 32 + i * 8 + (lane >> 2);
+            const int rx = tx * p.BW + (r & (p.BW - 1)), ry = ty * p.BH + (r >> p.BW_log2);
+            off16[i] = (((long long)img * p.Ho + ry) * p.Wo + rx) * p.ldo;
+            ok16 |= (unsigned)(tile_ok && (rx < p.Wo) && (ry < p.Ho)) << i;
+          }
+  #pragma unroll 1
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int col0 = n_tile * BLOCK_N + c0;
+            if (col0 >= p.Cout) break;                   // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);
+            if (p.residual) {                            // overlaps the TMEM load latency
+              const int seg = (lane & 7) * 4;
+  #pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (((ok32 >> i) & 1u) && col0 + seg < p.Cout)
+                  rv = *reinterpret_cast<const float4*>(p.residual + off32[i] + col0 + seg);
+                *reinterpret_cast<float4*>(st + (i * 4 + (lane >> 3)) * 36 + seg) = rv;
+              }
+              __syncwarp();
+            }
+            tmem_ld_wait();
+            float f[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            if (p.bias) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.Cout) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                }
+              }
+            }
+            if (p.residual) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(st + lane * 36 + j);
                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
               }
             }
-          }
-          if (p.residual) {
-            const float* r = p.residual + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < C::kChunk; j += 4) {
-              if (col0 + j < p.Cout) {
-                const float4 b = *reinterpret_cast<const float4*>(r + j);
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
+            if (p.relu) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < C::kChunk; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_f32) {
-            float* o = p.out_f32 + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < C::kChunk; j += 4)
-              if (col0 + j < p.Cout)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-          if (p.out_16) {
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0;
-#pragma unroll
-            for (int j = 0; j < C::kChunk; j += 8) {
-              if (col0 + j + 4 < p.Cout) {
+            if (p.gn_stats) {   // statistics of the finished fp32 values (bias and residual included)
+              if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
+              else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
+              else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
+            }
+            if (p.out_f32) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(st + lane * 36 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              __syncwarp();
+              const int seg = (lane & 7) * 4;
+  #pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (((ok32 >> i) & 1u) && col0 + seg < p.Cout)
+                  *reinterpret_cast<float4*>(p.out_f32 + off32[i] + col0 + seg) =
+                      *reinterpret_cast<const float4*>(st + (i * 4 + (lane >> 3)) * 36 + seg);
+              }
+              __syncwarp();
+            }
+            if (p.out_16) {
+              uint32_t* sw = reinterpret_cast<uint32_t*>(st);
+  #pragma unroll
+              for (int j = 0; j < 32; j += 8) {
                 uint4 u;
                 u.x = pack2_16(f[j], f[j + 1], p.fmt);     u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
                 u.z = pack2_16(f[j + 4], f[j + 5], p.fmt); u.w = pack2_16(f[j + 6], f[j + 7], p.fmt);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              } else if (col0 + j < p.Cout) {
-                uint2 u;
-                u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
-                *reinterpret_cast<uint2*>(o + j) = u;
+                *reinterpret_cast<uint4*>(sw + lane * 36 + (j >> 1)) = u;
+              }
+              __syncwarp();
+              const int seg = (lane & 3) * 8;            // 8 channels = 16 bytes
+              uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out_16);
+  #pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (((ok16 >> i) & 1u) && col0 + seg < p.Cout) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(sw + (i * 8 + (lane >> 2)) * 36 + (seg >> 1));
+                  if (col0 + seg + 4 < p.Cout) {
+                    *reinterpret_cast<uint4*>(o16 + off16[i] + col0 + seg) = u;
+                  } else {
+                    *reinterpret_cast<uint2*>(o16 + off16[i] + col0 + seg) = make_uint2(u.x, u.y);
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      } else {
+        // BLOCK_N == 16 (the 8-channel moments head): tiny, written straight from registers
+        uint32_t v[16];
+        tmem_ld16(t_row, v);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N;
+        if (row_ok && col0 < p.Cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (col0 + j < p.Cout) {
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+              if (p.residual) {
+                const float4 b = *reinterpret_cast<const float4*>(p.residual + row_off + col0 + j);
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+              if (p.relu) { f[j] = fmaxf(f[j], 0.f); f[j + 1] = fmaxf(f[j + 1], 0.f); f[j + 2] = fmaxf(f[j + 2], 0.f); f[j + 3] = fmaxf(f[j + 3], 0.f); }
+              if (p.out_f32)
+                *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (p.out_16) {
+                uint2 u; u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0 + j) = u;
               }
             }
           }
@@ -384,17 +678,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);   // the leader's MMA thread waits
+        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.gn_stats && gn_img >= 0) gn_flush();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();     // the peer may still be reading our smem / arriving on our barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (NCTA == 2) tmem_dealloc_2cta(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -406,6 +706,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;
 int g_num_sms = 0;
+int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
+int g_epi_mode = 1;     // SFV_EPI=0: write rows straight from registers; 1: coalesced via smem transpose
 
 int tc_init() {
   if (g_encode) return 0;
@@ -419,6 +721,8 @@ int tc_init() {
   SFV_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   SFV_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
   SFV_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  if (const char* e = getenv("SFV_NCTA")) g_ncta_max = atoi(e);
+  if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
@@ -439,20 +743,27 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
   return 0;
 }
 
-template <int BLOCK_N>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t s) {
-  using C = Cfg<BLOCK_N>;
+template <int BLOCK_N, int NCTA>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t s, const char* tag) {
+  using C = Cfg<BLOCK_N, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
-    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::kSmemBytes));
     attr_set = true;
   }
-  int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  const int max_units = g_num_sms / NCTA;
+  const int grid = (p.n_units < max_units ? p.n_units : max_units) * NCTA;
   // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
   const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
-  ProfScope prof(PROF_TC_GEMM, flops, s);
-  tc_gemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+  ProfScope prof(PROF_TC_GEMM, flops, s, tag);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA>, ma, mb, p));
   SFV_LAUNCH_OK();
   return 0;
 }
@@ -476,10 +787,15 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     strides[0] = 2;
     SFV_TRY(encode_map(&ma, a.fmt, 5, a.a, dims, strides, box));
   }
+  // CTA pairs (cta_group::2): two adjacent 128-pixel tiles share one B tile, halving the shared-memory
+  // operand traffic per MMA.  A batched B (attention) must be the same for both tiles of a pair.
+  const int tiles_m_per_img = ceil_div(a.Wo, a.BW) * ceil_div(a.Ho, a.BH);
+  int ncta = (g_ncta_max >= 2 && a.block_n >= 32 && (!a.b_batched || tiles_m_per_img % 2 == 0) &&
+              tiles_m_per_img * a.Nimg >= 2) ? 2 : 1;
   {
     cuuint64_t dims[3] = {a.b_k, a.b_rows, a.b_batched ? (cuuint64_t)a.Nimg : 1};
     cuuint64_t strides[3] = {2, a.b_row_stride, a.b_batched ? a.b_batch_stride : a.b_row_stride * a.b_rows};
-    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)a.block_n, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.block_n / ncta), 1};
     SFV_TRY(encode_map(&mb, a.fmt, 3, a.b, dims, strides, box));
   }
   TcParams p;
@@ -497,16 +813,36 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_tiles_m = p.tiles_x * p.tiles_y * a.Nimg;
   p.n_tiles_n = ceil_div(a.Cout, a.block_n);
   p.n_tiles = p.n_tiles_m * p.n_tiles_n;
+  p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
+  p.epi_mode = g_epi_mode;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
-  p.gn_stats = a.gn_stats; p.err = g_err_flag;
+  p.gn_stats = a.gn_stats; p.gn_cpg = a.gn_cpg; p.gn_groups = a.gn_cpg ? a.Cout / a.gn_cpg : 0;
+  if (a.gn_stats)
+    SFV_CHECK((a.gn_cpg == 4 || a.gn_cpg == 8 || a.gn_cpg == 16) && a.Cout % 32 == 0 && a.block_n >= 32 &&
+                  a.block_n / a.gn_cpg <= 64,
+              "tc_gemm: fused GroupNorm statistics need 4/8/16 channels per group (got %d)", a.gn_cpg);
+  p.err = g_err_flag;
+  char tag[64];
+  snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
+           a.ntaps, a.kchunks * 64, a.block_n, ncta, a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
+           a.gn_stats != nullptr);
+  if (ncta == 2) {
+    switch (a.block_n) {
+      case 256: return launch_cfg<256, 2>(ma, mb, p, s, tag);
+      case 128: return launch_cfg<128, 2>(ma, mb, p, s, tag);
+      case 64: return launch_cfg<64, 2>(ma, mb, p, s, tag);
+      case 32: return launch_cfg<32, 2>(ma, mb, p, s, tag);
+      default: break;
+    }
+  }
   switch (a.block_n) {
-    case 256: return launch_cfg<256>(ma, mb, p, s);
-    case 128: return launch_cfg<128>(ma, mb, p, s);
-    case 64: return launch_cfg<64>(ma, mb, p, s);
-    case 32: return launch_cfg<32>(ma, mb, p, s);
-    case 16: return launch_cfg<16>(ma, mb, p, s);
+    case 256: return launch_cfg<256, 1>(ma, mb, p, s, tag);
+    case 128: return launch_cfg<128, 1>(ma, mb, p, s, tag);
+    case 64: return launch_cfg<64, 1>(ma, mb, p, s, tag);
+    case 32: return launch_cfg<32, 1>(ma, mb, p, s, tag);
+    case 16: return launch_cfg<16, 1>(ma, mb, p, s, tag);
     default: return fail(SFV_ERR_INVALID, "tc_gemm: unsupported block_n %d", a.block_n);
   }
 }
