@@ -50,6 +50,7 @@ struct TcParams {
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
   int epi_mode;
+  unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
 };
 
@@ -95,6 +96,18 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
     }
   }
 }
+// One lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers
+// when the tcgen05 / TMA instructions are issued this way instead of from a divergent lane-0 branch).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -120,6 +133,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// shared -> global tile store (clips out-of-bounds elements); completion tracked by bulk groups
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// order generic-proxy shared-memory writes before async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
                "r"(ncols)
@@ -307,21 +343,33 @@ __device__ __forceinline__ void epi_stats_chunk(const float* f, bool valid, int 
   if ((lane & (32 / NV - 1)) == 0) acc_w[group0 * 2 + idx] += r;   // one owner lane per (group, moment): no race
 }
 
+// Epilogue staging (per epilogue warp): a ring of kResBufs fp32 tiles (32 rows x 128 B, 128B-swizzled) that
+// first receive the residual by TMA and then hold the fp32 output for the TMA store, and two 16-bit
+// output tiles (32 rows x 64 B, 64B-swizzled).
+constexpr int kResBufs = 3;
+constexpr int kEpiF32Bytes = 4 * kResBufs * 4096;
+constexpr int kEpiH16Bytes = 4 * 2 * 2048;
+constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias copies*/;
+
 template <int BLOCK_N, int NCTA>
 struct Cfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (BLOCK_N / NCTA) * kBlockK * 2;      // a CTA pair splits B's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kEpiBytes = BLOCK_N >= 32 ? (kEpiF32Bytes + kEpiH16Bytes) : 0;
+  static constexpr int kBudget = 232448 - 1024 - kAuxBytes - kEpiBytes;
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*GN partials*/ + 4 * 32 * 36 * 4 /*epilogue transpose tiles*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kAuxBytes + 1024 /*align slack*/;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 template <int BLOCK_N, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
+               const __grid_constant__ CUtensorMap tmO16, const TcParams p) {
   using C = Cfg<BLOCK_N, NCTA>;
   // NCTA == 2: the kernel runs as clusters of two CTAs (one SM pair) that share one
   // 256-pixel x BLOCK_N tile; rank 0 issues the MMAs for both (tcgen05 cta_group::2).
@@ -330,15 +378,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint8_t* epi_f32 = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are)
+  uint8_t* epi_h16 = epi_f32 + (C::kEpiBytes ? kEpiF32Bytes : 0);
+  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes + C::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 2 * C::kStages + 4);
+  uint64_t* res_bar = bars + 2 * C::kStages + 4;                           // [4 warps][kResBufs]
+  uint32_t* tmem_ptr = (uint32_t*)(res_bar + 4 * kResBufs);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
-  float* gn_acc = (float*)((uint8_t*)bars + 256);       // [4 epilogue warps][64 groups][2]
-  float* stage_all = gn_acc + 512;                       // [4 epilogue warps][32 rows][36 words]
+  float* gn_acc = (float*)((uint8_t*)bars + 512);        // [4 epilogue warps][64 groups][2]
+  float* bias_all = gn_acc + 512;                        // [4 epilogue warps][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -352,6 +403,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&tfull_bar[i]), 1);
       mbar_init(smem_u32(&tempty_bar[i]), 4 * NCTA);
     }
+    for (int i = 0; i < 4 * kResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     *abort_flag = 0;
     fence_barrier_init();
   }
@@ -368,10 +420,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int k_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
+      unsigned long long t_wait = 0, t_start = clock64();
       for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
         const int n_tile = unit % p.n_tiles_n;
         const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;   // may be a phantom tile (>= n_tiles_m): all OOB -> zeros
@@ -387,65 +440,80 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c1 = base[1] + p.tap_o[tap][1], c2 = base[2] + p.tap_o[tap][2];
           const int c3 = base[3] + p.tap_o[tap][3], c4 = base[4] + p.tap_o[tap][4];
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            const unsigned long long tw = p.dbg ? clock64() : 0;
             ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
+            if (p.dbg) t_wait += clock64() - tw;
             if (!ok) break;
             const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            if constexpr (NCTA == 2) {
-              // the leader's barrier collects the bytes of both CTAs' loads
-              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kStageBytes);
-              tma_load_5d_2cta(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
-              tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK,
-                               n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
-            } else {
-              mbar_arrive_expect_tx(fb, C::kStageBytes);
-              tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
-              tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
-                          p.b_batched ? img : 0);
+            if (elect_one_sync()) {
+              if constexpr (NCTA == 2) {
+                // the leader's barrier collects the bytes of both CTAs' loads
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kStageBytes);
+                tma_load_5d_2cta(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+                tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK,
+                                 n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
+              } else {
+                mbar_arrive_expect_tx(fb, C::kStageBytes);
+                tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+                tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
+                            p.b_batched ? img : 0);
+              }
             }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 1] = t_wait; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane; leader CTA only in pair mode) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (converged warp, one elected lane issues; leader CTA only in pair mode) =====
+    if (rank == 0) {
       const uint32_t idesc = make_idesc(p.fmt, BLOCK_N, kBlockM * NCTA);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
+      unsigned long long t_full = 0, t_tempty = 0, t_start = clock64();
       for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+        const unsigned long long tw0 = p.dbg ? clock64() : 0;
         ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, abort_flag, p.err, 2);
+        if (p.dbg) t_tempty += clock64() - tw0;
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int it = 0; it < k_iters; ++it) {
+          const unsigned long long tw = p.dbg ? clock64() : 0;
           ok = mbar_wait(smem_u32(&full_bar[stage]), phase, abort_flag, p.err, 3);
+          if (p.dbg) t_full += clock64() - tw;
           if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t da = make_smem_desc(sa);
           const uint64_t db = make_smem_desc(sa + C::kABytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            if constexpr (NCTA == 2)
-              umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+              if constexpr (NCTA == 2)
+                umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (NCTA == 2) {
+              umma_commit_2cta(smem_u32(&empty_bar[stage]), 3);             // frees the stage in both CTAs
+              if (it == k_iters - 1) umma_commit_2cta(smem_u32(&tfull_bar[acc]), 3);
+            } else {
+              umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when MMAs retire
+              if (it == k_iters - 1) umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete
+            }
           }
-          if constexpr (NCTA == 2) {
-            umma_commit_2cta(smem_u32(&empty_bar[stage]), 3);             // frees the stage in both CTAs
-            if (it == k_iters - 1) umma_commit_2cta(smem_u32(&tfull_bar[acc]), 3);
-          } else {
-            umma_commit(smem_u32(&empty_bar[stage]));           // frees the smem stage when MMAs retire
-            if (it == k_iters - 1) umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete
-          }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 3] = t_full; p.dbg[blockIdx.x * 8 + 4] = t_tempty; }
     }
   } else {
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
@@ -453,8 +521,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = quarter * 32 + lane;
     const int yy = row >> p.BW_log2;
     const int xx = row & (p.BW - 1);
+    // origin of this warp's 32 rows inside the tile (always a bx x by pixel rectangle, bx = min(BW, 32))
+    const int wx = (quarter * 32) & (p.BW - 1), wy = (quarter * 32) >> p.BW_log2;
     float* acc_w = gn_acc + quarter * 128;
-    float* stage_w = stage_all + quarter * (32 * 36);
+    float* bias_w = bias_all + quarter * 256;
     int gn_img = -1, gn_nt = 0;
     // GroupNorm partials are kept per warp in shared memory across the tiles of one image and
     // flushed with fp64 global atomics when the (image, n_tile) key changes.
@@ -471,8 +541,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();
     };
+    int bias_nt = -1;
+    auto load_bias = [&](int n_tile) {      // per-warp shared copy: L1 is ~empty with this much smem carved out
+      if (n_tile == bias_nt) return;
+      __syncwarp();
+      for (int j = lane; j < BLOCK_N; j += 32) {
+        const int c = n_tile * BLOCK_N + j;
+        bias_w[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+      }
+      bias_nt = n_tile;
+      __syncwarp();
+    };
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
+    unsigned long long t_tfull = 0, t_start = clock64();
+    constexpr int kNChunk = BLOCK_N / C::kChunk;
+    const bool use_tma = C::kChunk == 32 && p.epi_mode == 1;
+    const bool has_res = p.residual != nullptr;
+    // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
+    uint8_t* f32_w = epi_f32 + quarter * (kResBufs * 4096);
+    uint8_t* h16_w = epi_h16 + quarter * (2 * 2048);
+    uint64_t* res_bar_w = res_bar + quarter * kResBufs;
+    auto issue_residual = [&](int g) {      // whole warp calls; one elected lane issues
+      const int seq = g / kNChunk, c = g - seq * kNChunk;
+      const int unit = unit0 + seq * unit_step;
+      if (unit >= p.n_units) return;
+      const int n_tile = unit % p.n_tiles_n;
+      const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
+      const int col0 = n_tile * BLOCK_N + c * 32;
+      if (m_tile >= p.n_tiles_m || col0 >= p.Cout) return;     // consumer skips the same chunks
+      const int tx = m_tile % p.tiles_x;
+      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+      const int img = m_tile / (p.tiles_x * p.tiles_y);
+      const int slot = g % kResBufs;
+      if (elect_one_sync()) {
+        const uint32_t bar = smem_u32(&res_bar_w[slot]);
+        mbar_arrive_expect_tx(bar, 4096);
+        tma_load_4d(smem_u32(f32_w + slot * 4096), &tmR, bar, col0, tx * p.BW + wx, ty * p.BH + wy, img);
+      }
+      __syncwarp();
+    };
+    int g_cur = 0;                          // global chunk counter of this warp
+    if (use_tma && has_res) {
+      for (int g = 0; g < kResBufs - 1; ++g) issue_residual(g);
+    }
     for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
@@ -487,17 +599,98 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (gn_img >= 0) gn_flush();
         gn_img = img; gn_nt = n_tile;
       }
+      load_bias(n_tile);
+      const unsigned long long tw = p.dbg ? clock64() : 0;
       ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, abort_flag, p.err, 4);
+      if (p.dbg) t_tfull += clock64() - tw;
       if (!ok) break;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if constexpr (C::kChunk == 32) {
-        // Coalesced epilogue.  TMEM hands each lane one pixel row (32 consecutive channels), but
-        // writing rows straight from registers makes every warp store touch 32 different
-        // 128-byte lines.  Rows are therefore transposed through a per-warp shared-memory
-        // tile (row pitch 36 words: conflict-free for 128-bit accesses): global loads/stores
-        // are issued with 8 lanes per fp32 row (4 lanes per 16-bit row), i.e. whole lines.
-        if (p.epi_mode == 0) {
+        if (use_tma) {
+          // ---- asynchronous, coalesced epilogue: residual in by TMA (prefetched kResBufs-1 chunks ahead),
+          //      outputs out by TMA store; each lane only ever touches its own 128-byte (64-byte) row of the
+          //      swizzled staging tiles, so shared-memory accesses are conflict-free.
+          const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
+          const int sw16 = (lane >> 1) & 3;        // 64B swizzle:  chunk j of row r lives at j ^ ((r >> 1) & 3)
+#pragma unroll 1
+          for (int c = 0; c < kNChunk; ++c, ++g_cur) {
+            const int c0 = c * 32;
+            const int col0 = n_tile * BLOCK_N + c0;
+            const bool chunk_ok = tile_ok && col0 < p.Cout;     // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);
+            const int slot = g_cur % kResBufs;
+            uint8_t* fb = f32_w + slot * 4096 + lane * 128;
+            float f[32];
+            if (has_res && chunk_ok) {
+              ok = mbar_wait(smem_u32(&res_bar_w[slot]), (uint32_t)((g_cur / kResBufs) & 1), abort_flag, p.err, 5);
+              if (!ok) break;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r4 = *reinterpret_cast<const float4*>(fb + ((j ^ sw) << 4));
+                f[4 * j] = r4.x; f[4 * j + 1] = r4.y; f[4 * j + 2] = r4.z; f[4 * j + 3] = r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+            tmem_ld_wait();
+            if (chunk_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_w + c0 + j);
+                f[j] += fmaf(__uint_as_float(v[j]), p.alpha, b.x);
+                f[j + 1] += fmaf(__uint_as_float(v[j + 1]), p.alpha, b.y);
+                f[j + 2] += fmaf(__uint_as_float(v[j + 2]), p.alpha, b.z);
+                f[j + 3] += fmaf(__uint_as_float(v[j + 3]), p.alpha, b.w);
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (p.gn_stats) {   // statistics of the finished fp32 values (bias and residual included)
+                if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
+                else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
+                else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
+              }
+              if (p.out_f32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(fb + ((j ^ sw) << 4)) =
+                      make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
+              uint8_t* hb = h16_w + (g_cur & 1) * 2048 + lane * 64;
+              if (p.out_16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 u;
+                  u.x = pack2_16(f[8 * j], f[8 * j + 1], p.fmt);     u.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt);
+                  u.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt); u.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt);
+                  *reinterpret_cast<uint4*>(hb + ((j ^ sw16) << 4)) = u;
+                }
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (elect_one_sync()) {
+                const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
+                if (p.out_f32) tma_store_4d(&tmO32, smem_u32(f32_w + slot * 4096), col0, ox, oy, img);
+                if (p.out_16) tma_store_4d(&tmO16, smem_u32(h16_w + (g_cur & 1) * 2048), col0, ox, oy, img);
+                tma_store_commit();
+                tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
+              }
+              __syncwarp();
+            }
+            if (has_res) {
+              if (!chunk_ok) {                 // skipped chunk: still make sure the slot about to be refilled is free
+                if (elect_one_sync()) tma_store_wait_read<1>();
+                __syncwarp();
+              }
+              issue_residual(g_cur + kResBufs - 1);   // refills the slot freed by the wait above
+            }
+          }
+          if (!ok) break;
+        } else {
           // reference epilogue: every lane writes its own pixel row straight from registers
 #pragma unroll 1
           for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -508,15 +701,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_wait();
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha + bias_w[c0 + j];
             if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 if (col0 + j < p.Cout) {
-                  if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                    f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-                  }
                   if (p.residual) {
                     const float4 b = *reinterpret_cast<const float4*>(p.residual + row_off + col0 + j);
                     f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
@@ -537,111 +726,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
             }
           }
-        } else {
-          float* st = stage_w;
-          // rows this lane serves in the transposed patterns
-          long long off32[8]; long long off16[4];
-          unsigned ok32 = 0, ok16 = 0;
-  #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = quarter * 32 + i * 4 + (lane >> 3);
-            const int rx = tx * p.BW + (r & (p.BW - 1)), ry = ty * p.BH + (r >> p.BW_log2);
-            off32[i] = (((long long)img * p.Ho + ry) * p.Wo + rx) * p.ldo;
-            ok32 |= (unsigned)(tile_ok && (rx < p.Wo) && (ry < p.Ho)) << i;
-          }
-  #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = quarter * 32 + i * 8 + (lane >> 2);
-            const int rx = tx * p.BW + (r & (p.BW - 1)), ry = ty * p.BH + (r >> p.BW_log2);
-            off16[i] = (((long long)img * p.Ho + ry) * p.Wo + rx) * p.ldo;
-            ok16 |= (unsigned)(tile_ok && (rx < p.Wo) && (ry < p.Ho)) << i;
-          }
-  #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            const int col0 = n_tile * BLOCK_N + c0;
-            if (col0 >= p.Cout) break;                   // warp-uniform
-            uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
-            if (p.residual) {                            // overlaps the TMEM load latency
-              const int seg = (lane & 7) * 4;
-  #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (((ok32 >> i) & 1u) && col0 + seg < p.Cout)
-                  rv = *reinterpret_cast<const float4*>(p.residual + off32[i] + col0 + seg);
-                *reinterpret_cast<float4*>(st + (i * 4 + (lane >> 3)) * 36 + seg) = rv;
-              }
-              __syncwarp();
-            }
-            tmem_ld_wait();
-            float f[32];
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-            if (p.bias) {
-  #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (col0 + j < p.Cout) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-                }
-              }
-            }
-            if (p.residual) {
-  #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(st + lane * 36 + j);
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-            if (p.relu) {
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (p.gn_stats) {   // statistics of the finished fp32 values (bias and residual included)
-              if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
-              else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
-              else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
-            }
-            if (p.out_f32) {
-  #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(st + lane * 36 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              __syncwarp();
-              const int seg = (lane & 7) * 4;
-  #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (((ok32 >> i) & 1u) && col0 + seg < p.Cout)
-                  *reinterpret_cast<float4*>(p.out_f32 + off32[i] + col0 + seg) =
-                      *reinterpret_cast<const float4*>(st + (i * 4 + (lane >> 3)) * 36 + seg);
-              }
-              __syncwarp();
-            }
-            if (p.out_16) {
-              uint32_t* sw = reinterpret_cast<uint32_t*>(st);
-  #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack2_16(f[j], f[j + 1], p.fmt);     u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
-                u.z = pack2_16(f[j + 4], f[j + 5], p.fmt); u.w = pack2_16(f[j + 6], f[j + 7], p.fmt);
-                *reinterpret_cast<uint4*>(sw + lane * 36 + (j >> 1)) = u;
-              }
-              __syncwarp();
-              const int seg = (lane & 3) * 8;            // 8 channels = 16 bytes
-              uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out_16);
-  #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (((ok16 >> i) & 1u) && col0 + seg < p.Cout) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(sw + (i * 8 + (lane >> 2)) * 36 + (seg >> 1));
-                  if (col0 + seg + 4 < p.Cout) {
-                    *reinterpret_cast<uint4*>(o16 + off16[i] + col0 + seg) = u;
-                  } else {
-                    *reinterpret_cast<uint2*>(o16 + off16[i] + col0 + seg) = make_uint2(u.x, u.y);
-                  }
-                }
-              }
-              __syncwarp();
-            }
-          }
         }
       } else {
         // BLOCK_N == 16 (the 8-channel moments head): tiny, written straight from registers
@@ -652,14 +736,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row_ok && col0 < p.Cout) {
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha + bias_w[j];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (col0 + j < p.Cout) {
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
               if (p.residual) {
                 const float4 b = *reinterpret_cast<const float4*>(p.residual + row_off + col0 + j);
                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
@@ -684,7 +764,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (use_tma) {      // staging tiles must outlive the bulk stores that read them
+      if (elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
     if (p.gn_stats && gn_img >= 0) gn_flush();
+    if (p.dbg && warp == 2 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 6] = t_tfull; }
   }
 
   tc_fence_before();
@@ -707,7 +792,8 @@ EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;
 int g_num_sms = 0;
 int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
-int g_epi_mode = 1;     // SFV_EPI=0: write rows straight from registers; 1: coalesced via smem transpose
+int g_epi_mode = 1;
+unsigned long long* g_dbg = nullptr;   // SFV_TC_DEBUG=1: per-CTA role cycle counters, printed after each launch (synchronous)     // SFV_EPI=0: write rows straight from registers; 1: coalesced via smem transpose
 
 int tc_init() {
   if (g_encode) return 0;
@@ -723,28 +809,33 @@ int tc_init() {
   SFV_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
   if (const char* e = getenv("SFV_NCTA")) g_ncta_max = atoi(e);
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
+  if (const char* e = getenv("SFV_TC_DEBUG")) { if (atoi(e)) SFV_CUDA(cudaMalloc(&g_dbg, 8 * 8 * 256)); }
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
 
 int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes = 128, bool f32 = false) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (((uintptr_t)ptr & 15) != 0) return fail(SFV_ERR_INVALID, "TMA base not 16B aligned");
   for (int i = 1; i < rank; ++i)
     if (strides_bytes[i] % 16 != 0)
       return fail(SFV_ERR_INVALID, "TMA stride %d = %llu not a multiple of 16 B", i,
                   (unsigned long long)strides_bytes[i]);
-  CUresult r = g_encode(m, fmt == FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+  const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                     : (fmt == FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  CUresult r = g_encode(m, dt,
                         (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes + 1, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SFV_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
   return 0;
 }
 
 template <int BLOCK_N, int NCTA>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t s, const char* tag) {
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo32,
+               const CUtensorMap& mo16, const TcParams& p, cudaStream_t s, const char* tag) {
   using C = Cfg<BLOCK_N, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -763,8 +854,19 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA>, ma, mb, p));
+  if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 8 * 256, s));
+  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA>, ma, mb, mr, mo32, mo16, p));
   SFV_LAUNCH_OK();
+  if (g_dbg) {
+    std::vector<unsigned long long> h(8 * 256);
+    SFV_CUDA(cudaStreamSynchronize(s));
+    SFV_CUDA(cudaMemcpy(h.data(), g_dbg, 8 * 8 * 256, cudaMemcpyDeviceToHost));
+    double a[8] = {0}; int n = 0;
+    for (int b = 0; b < grid; b += NCTA) { for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k]; ++n; }
+    for (int k = 0; k < 8; ++k) a[k] /= n;
+    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f\n",
+            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
   return 0;
 }
 
@@ -775,6 +877,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_CHECK(a.BW * a.BH == kBlockM && (a.BW & (a.BW - 1)) == 0, "tc_gemm: bad tile %dx%d", a.BW, a.BH);
   SFV_CHECK(a.ntaps >= 1 && a.ntaps <= 9 && a.kchunks >= 1, "tc_gemm: bad taps/kchunks");
   SFV_CHECK(a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0");
+  SFV_CHECK(a.block_n <= 256, "tc_gemm: block_n > 256");
   SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
   CUtensorMap ma, mb;
   {
@@ -815,6 +918,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_tiles = p.n_tiles_m * p.n_tiles_n;
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
   p.epi_mode = g_epi_mode;
+  p.dbg = g_dbg;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
@@ -824,25 +928,41 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
                   a.block_n / a.gn_cpg <= 64,
               "tc_gemm: fused GroupNorm statistics need 4/8/16 channels per group (got %d)", a.gn_cpg);
   p.err = g_err_flag;
+  // epilogue tensor maps: per-warp boxes of 32 channels x (bx x by) pixels over the output / residual tensors
+  CUtensorMap mr = ma, mo32 = ma, mo16 = ma;
+  const bool tma_epi = g_epi_mode == 1 && a.block_n >= 32 && a.ldo % 8 == 0 &&
+                       (!a.out_f32 || ((uintptr_t)a.out_f32 & 15) == 0) && (!a.out_16 || ((uintptr_t)a.out_16 & 15) == 0) &&
+                       (!a.residual || ((uintptr_t)a.residual & 15) == 0);
+  p.epi_mode = tma_epi ? 1 : 0;
+  if (tma_epi) {
+    const cuuint32_t bx = a.BW < 32 ? a.BW : 32, by = 32 / bx;
+    cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.Nimg};
+    cuuint32_t box[4] = {32, bx, by, 1};
+    cuuint64_t st32[4] = {4, (cuuint64_t)a.ldo * 4, (cuuint64_t)a.ldo * 4 * a.Wo, (cuuint64_t)a.ldo * 4 * a.Wo * a.Ho};
+    cuuint64_t st16[4] = {2, (cuuint64_t)a.ldo * 2, (cuuint64_t)a.ldo * 2 * a.Wo, (cuuint64_t)a.ldo * 2 * a.Wo * a.Ho};
+    if (a.residual) SFV_TRY(encode_map(&mr, a.fmt, 4, a.residual, dims, st32, box, 128, true));
+    if (a.out_f32) SFV_TRY(encode_map(&mo32, a.fmt, 4, a.out_f32, dims, st32, box, 128, true));
+    if (a.out_16) SFV_TRY(encode_map(&mo16, a.fmt, 4, a.out_16, dims, st16, box, 64, false));
+  }
   char tag[64];
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
   if (ncta == 2) {
     switch (a.block_n) {
-      case 256: return launch_cfg<256, 2>(ma, mb, p, s, tag);
-      case 128: return launch_cfg<128, 2>(ma, mb, p, s, tag);
-      case 64: return launch_cfg<64, 2>(ma, mb, p, s, tag);
-      case 32: return launch_cfg<32, 2>(ma, mb, p, s, tag);
+      case 256: return launch_cfg<256, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
+      case 128: return launch_cfg<128, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
+      case 64: return launch_cfg<64, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
+      case 32: return launch_cfg<32, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
       default: break;
     }
   }
   switch (a.block_n) {
-    case 256: return launch_cfg<256, 1>(ma, mb, p, s, tag);
-    case 128: return launch_cfg<128, 1>(ma, mb, p, s, tag);
-    case 64: return launch_cfg<64, 1>(ma, mb, p, s, tag);
-    case 32: return launch_cfg<32, 1>(ma, mb, p, s, tag);
-    case 16: return launch_cfg<16, 1>(ma, mb, p, s, tag);
+    case 256: return launch_cfg<256, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
+    case 128: return launch_cfg<128, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
+    case 64: return launch_cfg<64, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
+    case 32: return launch_cfg<32, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
+    case 16: return launch_cfg<16, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
     default: return fail(SFV_ERR_INVALID, "tc_gemm: unsupported block_n %d", a.block_n);
   }
 }

@@ -52,7 +52,10 @@ def main():
                 ("ncta1_epi1_st0", dict(SFV_NCTA="1", SFV_EPI="1", SFV_FUSED_STATS="0")),
                 ("ncta1_epi1_st1", dict(SFV_NCTA="1", SFV_EPI="1", SFV_FUSED_STATS="1")),
                 ("ncta2_epi0_st1", dict(SFV_NCTA="2", SFV_EPI="0", SFV_FUSED_STATS="1")),
-                ("ncta2_epi1_st1", dict(SFV_NCTA="2", SFV_EPI="1", SFV_FUSED_STATS="1"))]
+                ("ncta2_epi1_st1", dict(SFV_NCTA="2", SFV_EPI="1", SFV_FUSED_STATS="1")),
+                ("x_tmemonly", dict(SFV_NCTA="1", SFV_EPI="2", SFV_FUSED_STATS="1")),
+                ("x_nostore", dict(SFV_NCTA="1", SFV_EPI="3", SFV_FUSED_STATS="1")),
+                ("x_nostore_nostats", dict(SFV_NCTA="1", SFV_EPI="3", SFV_FUSED_STATS="0"))]
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     res = {}
     for name, env in variants:
