@@ -160,7 +160,7 @@ class AutoencoderKL(nn.Module):
         self.precision = (precision or os.environ.get("SFV_PRECISION", "bf16")).lower()
         if self.precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
-        self.chunk = chunk
+        self.chunk = chunk or int(os.environ.get("SFV_CHUNK", "0")) or None
         _build_tree(self, encoder_param_shapes())
         self._handle = None
         self._ws = _lib.Workspace()

@@ -86,8 +86,23 @@ __device__ __forceinline__ float f16_to_32(uint16_t v, int fmt) {
   __half h = *reinterpret_cast<__half*>(&v);
   return __half2float(h);
 }
+// two fp32 -> packed 16-bit pair (a in the low half), one F2FP instruction; fp16 saturates at +-65504
 __device__ __forceinline__ uint32_t pack2_16(float a, float b, int fmt) {
-  return (uint32_t)f32_to_16(a, fmt) | ((uint32_t)f32_to_16(b, fmt) << 16);
+  uint32_t r;
+  if (fmt == FMT_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// packed 16-bit pair -> two fp32
+__device__ __forceinline__ void unpack2_16(uint32_t w, int fmt, float& a, float& b) {
+  if (fmt == FMT_BF16) {
+    a = __uint_as_float(w << 16);
+    b = __uint_as_float(w & 0xFFFF0000u);
+  } else {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    const float2 f = __half22float2(h);
+    a = f.x; b = f.y;
+  }
 }
 
 // ---- bump allocator over the caller's workspace ----------------------------
@@ -164,6 +179,7 @@ struct TcGemmArgs {
   const void* b; unsigned long long b_rows, b_k; unsigned long long b_row_stride, b_batch_stride;
   int b_batched;
   int ntaps; TcTap taps[9]; int tap_k[9];  // tap_k: k offset in B for this tap
+  int halo_ok;                       // 3x3 stride-1 conv whose taps are row-major with x offsets -1,0,+1
   int kchunks;                       // 64-wide K chunks per tap
   // tiling of the output
   int BW, BH;                        // tile = BH rows x BW cols (BH*BW == 128)

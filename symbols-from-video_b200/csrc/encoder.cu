@@ -215,6 +215,7 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
     a.a_strides[1] = (unsigned long long)Cin * 2; a.a_strides[2] = a.a_strides[1] * W; a.a_strides[3] = a.a_strides[2] * H;
     a.a_box[0] = 64; a.a_box[1] = a.BW; a.a_box[2] = a.BH; a.a_box[3] = 1;
     a.dim_x = 1; a.dim_y = 2; a.dim_n = 3;
+    a.halo_ok = (ks == 3 && pad_lo == 1 && pad_hi == 1);
     a.ntaps = ks * ks;
     for (int r = 0; r < ks; ++r)
       for (int c = 0; c < ks; ++c) {

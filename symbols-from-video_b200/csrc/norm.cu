@@ -82,12 +82,8 @@ template <bool IN16>
 __device__ __forceinline__ void load8(const void* base, long long idx, int fmt, float v[8]) {
   if (IN16) {
     const uint4 u = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[2 * j] = f16_to_32((uint16_t)(w[j] & 0xFFFF), fmt);
-      v[2 * j + 1] = f16_to_32((uint16_t)(w[j] >> 16), fmt);
-    }
+    unpack2_16(u.x, fmt, v[0], v[1]); unpack2_16(u.y, fmt, v[2], v[3]);
+    unpack2_16(u.z, fmt, v[4], v[5]); unpack2_16(u.w, fmt, v[6], v[7]);
   } else {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
     const float4 b = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4));
@@ -128,7 +124,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = min(p0 + (long long)pix_per_block, HW);
   const long long base = (long long)n * HW * C + tc * 8;
-  constexpr int U = 4;
+  constexpr int U = IN16 ? 8 : 4;      // keep >= 128 B per thread in flight
   for (long long p = p0 + tr; p < p1; p += (long long)rows * U) {
     float v[U][8];
 #pragma unroll
@@ -314,7 +310,7 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
     long long want = (HW * N + 148 * 16 - 1) / (148 * 16);
     int ppb = (int)(want < 64 ? 64 : (want > 1024 ? 1024 : want));
     const int rows = 256 / (C / 8);
-    ppb = (ppb + rows * 4 - 1) / (rows * 4) * (rows * 4);
+    ppb = (ppb + rows * 8 - 1) / (rows * 8) * (rows * 8);
     dim3 grid((unsigned)((HW + ppb - 1) / ppb), N);
     if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
     else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);

@@ -50,6 +50,7 @@ struct TcParams {
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
   int epi_mode;
+  int halo_base_offset;
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
 };
@@ -276,8 +277,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t
 
 // UMMA shared-memory descriptor, K-major, 128-byte swizzle, 8-row atoms 1024 B apart
 // (bit layout: cute::UMMA::SmemDescriptor; version=1 for sm_100).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7u) << 49;       // swizzle phase of a start address that is not 1024 B aligned
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
   d |= (uint64_t)1 << 16;                        // leading byte offset (unused for SW128 K-major)
   d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
@@ -351,11 +353,18 @@ constexpr int kEpiF32Bytes = 4 * kResBufs * 4096;
 constexpr int kEpiH16Bytes = 4 * 2 * 2048;
 constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias copies*/;
 
-template <int BLOCK_N, int NCTA>
+// HALO: for 3x3 stride-1 convolutions tiled as 128-pixel row segments, one TMA box of 130 pixels feeds the
+// three horizontal taps of a filter row; the MMAs read it at start addresses shifted by one pixel
+// (128 B) per tap.  Cuts the A operand's TMA->smem traffic 3x on the layers where the shared-memory
+// port, not the tensor pipe, bounds the main loop (Cout = 128).
+template <int BLOCK_N, int NCTA, bool HALO = false>
 struct Cfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kGroup = HALO ? 3 : 1;                           // filter taps per pipeline stage
+  static constexpr int kATxBytes = HALO ? 130 * 128 : kBlockM * kBlockK * 2;
+  static constexpr int kABytes = HALO ? 17 * 1024 : kBlockM * kBlockK * 2;   // keeps the B tiles 1024 B aligned
   static constexpr int kBBytes = (BLOCK_N / NCTA) * kBlockK * 2;      // a CTA pair splits B's rows
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kABytes + kGroup * kBBytes;
+  static constexpr int kTxBytes = kATxBytes + kGroup * kBBytes;
   static constexpr int kEpiBytes = BLOCK_N >= 32 ? (kEpiF32Bytes + kEpiH16Bytes) : 0;
   static constexpr int kBudget = 232448 - 1024 - kAuxBytes - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -365,12 +374,12 @@ struct Cfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-template <int BLOCK_N, int NCTA>
+template <int BLOCK_N, int NCTA, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
                const __grid_constant__ CUtensorMap tmO16, const TcParams p) {
-  using C = Cfg<BLOCK_N, NCTA>;
+  using C = Cfg<BLOCK_N, NCTA, HALO>;
   // NCTA == 2: the kernel runs as clusters of two CTAs (one SM pair) that share one
   // 256-pixel x BLOCK_N tile; rank 0 issues the MMAs for both (tcgen05 cta_group::2).
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
@@ -417,7 +426,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (NCTA == 2) cluster_sync_all();     // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int k_iters = p.ntaps * p.kchunks;
+  const int k_iters = (p.ntaps / C::kGroup) * p.kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
@@ -436,7 +445,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.dim_y >= 0) base[p.dim_y] += ty * p.BH;
         if (p.dim_n >= 0) base[p.dim_n] += img;
         if (p.dim_n < 0 && p.dim_y < 0 && m_tile >= p.n_tiles_m) base[p.dim_x] = 0x3fffffff;   // phantom row block
-        for (int tap = 0; tap < p.ntaps && ok; ++tap) {
+        for (int tap = 0; tap < p.ntaps && ok; tap += C::kGroup) {
           const int c1 = base[1] + p.tap_o[tap][1], c2 = base[2] + p.tap_o[tap][2];
           const int c3 = base[3] + p.tap_o[tap][3], c4 = base[4] + p.tap_o[tap][4];
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -447,17 +456,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (elect_one_sync()) {
+              // HALO: tap is the left tap of a filter row; its box is 130 pixels wide and serves taps tap..tap+2
               if constexpr (NCTA == 2) {
                 // the leader's barrier collects the bytes of both CTAs' loads
-                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kStageBytes);
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kTxBytes);
                 tma_load_5d_2cta(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
-                tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK,
-                                 n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
+#pragma unroll
+                for (int g = 0; g < C::kGroup; ++g)
+                  tma_load_3d_2cta(sa + C::kABytes + g * C::kBBytes, &tmB, fb, p.tap_k[tap + g] + kc * kBlockK,
+                                   n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
               } else {
-                mbar_arrive_expect_tx(fb, C::kStageBytes);
+                mbar_arrive_expect_tx(fb, C::kTxBytes);
                 tma_load_5d(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
-                tma_load_3d(sa + C::kABytes, &tmB, fb, p.tap_k[tap] + kc * kBlockK, n_tile * BLOCK_N,
-                            p.b_batched ? img : 0);
+#pragma unroll
+                for (int g = 0; g < C::kGroup; ++g)
+                  tma_load_3d(sa + C::kABytes + g * C::kBBytes, &tmB, fb, p.tap_k[tap + g] + kc * kBlockK,
+                              n_tile * BLOCK_N, p.b_batched ? img : 0);
               }
             }
             __syncwarp();
@@ -489,16 +503,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = make_smem_desc(sa);
-          const uint64_t db = make_smem_desc(sa + C::kABytes);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-              if constexpr (NCTA == 2)
-                umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-              else
-                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int g = 0; g < C::kGroup; ++g) {
+              // HALO: tap g of the filter row reads the same box one pixel (128 B) further right.  The 128B swizzle
+              // is applied to absolute smem address bits by both TMA and UMMA, so a start address that is
+              // 128-byte (not 1024-byte) aligned needs no descriptor base offset (verified on B200).
+              const uint64_t da = make_smem_desc(sa + g * 128, p.halo_base_offset ? (uint32_t)g : 0u);
+              const uint64_t db = make_smem_desc(sa + C::kABytes + g * C::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+                const uint32_t accum = (it > 0 || g > 0 || k > 0) ? 1u : 0u;
+                if constexpr (NCTA == 2)
+                  umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+                else
+                  umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+              }
             }
             if constexpr (NCTA == 2) {
               umma_commit_2cta(smem_u32(&empty_bar[stage]), 3);             // frees the stage in both CTAs
@@ -792,6 +813,9 @@ EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;
 int g_num_sms = 0;
 int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
+int g_halo = 1;         // SFV_HALO=0 disables the shared A halo box
+int g_halo_boff = 0;    // descriptor base-offset for the shifted taps: measured WRONG on B200 (the swizzle is a function of
+                        // the absolute smem address bits), so it stays 0; SFV_HALO_BOFF=1 reproduces the failing variant
 int g_epi_mode = 1;
 unsigned long long* g_dbg = nullptr;   // SFV_TC_DEBUG=1: per-CTA role cycle counters, printed after each launch (synchronous)     // SFV_EPI=0: write rows straight from registers; 1: coalesced via smem transpose
 
@@ -809,6 +833,8 @@ int tc_init() {
   SFV_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
   if (const char* e = getenv("SFV_NCTA")) g_ncta_max = atoi(e);
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
+  if (const char* e = getenv("SFV_HALO")) g_halo = atoi(e);
+  if (const char* e = getenv("SFV_HALO_BOFF")) g_halo_boff = atoi(e);
   if (const char* e = getenv("SFV_TC_DEBUG")) { if (atoi(e)) SFV_CUDA(cudaMalloc(&g_dbg, 8 * 8 * 256)); }
   g_encode = (EncodeTiledFn)fn;
   return 0;
@@ -833,13 +859,13 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
   return 0;
 }
 
-template <int BLOCK_N, int NCTA>
+template <int BLOCK_N, int NCTA, bool HALO = false>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo32,
                const CUtensorMap& mo16, const TcParams& p, cudaStream_t s, const char* tag) {
-  using C = Cfg<BLOCK_N, NCTA>;
+  using C = Cfg<BLOCK_N, NCTA, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::kSmemBytes));
     attr_set = true;
   }
@@ -855,7 +881,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 8 * 256, s));
-  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA>, ma, mb, mr, mo32, mo16, p));
+  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO>, ma, mb, mr, mo32, mo16, p));
   SFV_LAUNCH_OK();
   if (g_dbg) {
     std::vector<unsigned long long> h(8 * 256);
@@ -880,6 +906,9 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_CHECK(a.block_n <= 256, "tc_gemm: block_n > 256");
   SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
   CUtensorMap ma, mb;
+  // HALO variant: 3x3 stride-1 conv, 128-pixel row-segment tiles, taps ordered row-major with dx = -1,0,+1
+  const bool halo = g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
+                    a.block_n == 128 && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
   {
     cuuint64_t dims[5], strides[5]; cuuint32_t box[5];
     for (int i = 0; i < 5; ++i) {
@@ -887,6 +916,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
       strides[i] = i < a.a_rank ? a.a_strides[i] : (i > 0 ? strides[i - 1] * dims[i - 1] : 2);
       box[i] = i < a.a_rank ? a.a_box[i] : 1;
     }
+    if (halo) box[a.dim_x] = 130;
     strides[0] = 2;
     SFV_TRY(encode_map(&ma, a.fmt, 5, a.a, dims, strides, box));
   }
@@ -919,6 +949,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
   p.epi_mode = g_epi_mode;
   p.dbg = g_dbg;
+  p.halo_base_offset = g_halo_boff;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
@@ -945,9 +976,10 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     if (a.out_16) SFV_TRY(encode_map(&mo16, a.fmt, 4, a.out_16, dims, st16, box, 64, false));
   }
   char tag[64];
-  snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
-           a.ntaps, a.kchunks * 64, a.block_n, ncta, a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
+  snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
+           a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
+  if (halo) return launch_cfg<128, 2, true>(ma, mb, mr, mo32, mo16, p, s, tag);
   if (ncta == 2) {
     switch (a.block_n) {
       case 256: return launch_cfg<256, 2>(ma, mb, mr, mo32, mo16, p, s, tag);

@@ -82,6 +82,9 @@ CONV_SHAPES = [
     (2, 16, 32, 256, 256, 3, 2, (1, 1), False),   # RBVAE style stride 2 pad 1
     (1, 8, 8, 512, 8, 3, 1, (1, 1), False),       # head: Cout 8 padded to 16
     (3, 8, 16, 512, 1024, 1, 1, (0, 0), False),   # fused q|k projection shape
+    (1, 6, 256, 128, 128, 3, 1, (1, 1), True),    # Cout 128, 128-pixel row tiles: shared A halo box (3 taps per stage)
+    (2, 5, 128, 64, 128, 3, 1, (1, 1), False),    # halo variant, one k-chunk, odd tile count (phantom CTA-pair tile)
+    (1, 3, 200, 128, 128, 3, 1, (1, 1), True),    # halo variant with a ragged right edge
 ]
 # the distinct (M,N,K) GEMM shapes of SURVEY 2a at 64x64 input resolution
 LAYER_SHAPES_64 = [

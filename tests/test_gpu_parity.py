@@ -9,7 +9,7 @@ def _c():
     return gpu_checks
 
 
-@pytest.mark.parametrize("shape", range(10))
+@pytest.mark.parametrize("shape", range(13))
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
 def test_conv_tile_geometries(prec, shape):
     c = _c()
