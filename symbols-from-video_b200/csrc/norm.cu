@@ -92,11 +92,11 @@ __device__ __forceinline__ void load8(const void* base, long long idx, int fmt, 
 }
 
 template <bool IN16, bool OUT16>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, const double* __restrict__ stats,
-                                                       const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, void* __restrict__ y,
-                                                       int fmt, long long HW, int C, int G, float eps,
-                                                       int do_silu, int pix_per_block) {
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict__ x, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, void* __restrict__ y,
+                                                          int fmt, long long HW, int C, int G, float eps,
+                                                          int do_silu, int pix_per_block) {
   __shared__ float sh_mean[64], sh_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
@@ -124,33 +124,54 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = min(p0 + (long long)pix_per_block, HW);
   const long long base = (long long)n * HW * C + tc * 8;
-  constexpr int U = IN16 ? 8 : 4;      // keep >= 128 B per thread in flight
+  // 128 bytes per thread in flight (x 1024 resident threads per SM): the raw words stay packed in
+  // registers until they are consumed, so the kernel fits 64 registers / 4 blocks per SM.
+  constexpr int U = IN16 ? 8 : 4;
+  constexpr int W = IN16 ? 1 : 2;         // uint4 words per pixel per thread
   for (long long p = p0 + tr; p < p1; p += (long long)rows * U) {
-    float v[U][8];
+    uint4 raw[U][W];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long pp = p + (long long)u * rows;
-      if (pp < p1) load8<IN16>(x, base + pp * C, fmt, v[u]);
+      if (pp < p1) {
+        if (IN16) {
+          raw[u][0] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + base + pp * C));
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(x) + base + pp * C);
+          raw[u][0] = __ldcs(src);
+          raw[u][W - 1] = __ldcs(src + 1);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long pp = p + (long long)u * rows;
       if (pp >= p1) break;
+      float v[8];
+      if (IN16) {
+        unpack2_16(raw[u][0].x, fmt, v[0], v[1]); unpack2_16(raw[u][0].y, fmt, v[2], v[3]);
+        unpack2_16(raw[u][0].z, fmt, v[4], v[5]); unpack2_16(raw[u][0].w, fmt, v[6], v[7]);
+      } else {
+        v[0] = __uint_as_float(raw[u][0].x); v[1] = __uint_as_float(raw[u][0].y);
+        v[2] = __uint_as_float(raw[u][0].z); v[3] = __uint_as_float(raw[u][0].w);
+        v[4] = __uint_as_float(raw[u][W - 1].x); v[5] = __uint_as_float(raw[u][W - 1].y);
+        v[6] = __uint_as_float(raw[u][W - 1].z); v[7] = __uint_as_float(raw[u][W - 1].w);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(v[u][j], sc[j], sf[j]);
-        v[u][j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
+        const float t = fmaf(v[j], sc[j], sf[j]);
+        v[j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
       }
       const long long idx = base + pp * C;
       if (OUT16) {
         uint4 o;
-        o.x = pack2_16(v[u][0], v[u][1], fmt); o.y = pack2_16(v[u][2], v[u][3], fmt);
-        o.z = pack2_16(v[u][4], v[u][5], fmt); o.w = pack2_16(v[u][6], v[u][7], fmt);
+        o.x = pack2_16(v[0], v[1], fmt); o.y = pack2_16(v[2], v[3], fmt);
+        o.z = pack2_16(v[4], v[5], fmt); o.w = pack2_16(v[6], v[7], fmt);
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + idx) = o;
       } else {
         float* o = reinterpret_cast<float*>(y) + idx;
-        *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
   }
