@@ -73,7 +73,7 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
                        SfvEncoder** out);
 void sfv_encoder_destroy(SfvEncoder* enc);
 int sfv_encoder_precision(const SfvEncoder* enc);
-/* Frames pushed through the network together (default 8): bounds the workspace
+/* Frames pushed through the network together (default 16): bounds the workspace
  * and keeps the deeper levels L2-resident; B larger than this is processed in
  * slices inside one sfv_encoder_forward_* call. */
 int sfv_encoder_set_chunk(SfvEncoder* enc, int32_t frames);
@@ -141,6 +141,11 @@ int sfv_resize_workspace_bytes(int32_t B, int32_t Hs, int32_t Ws, int32_t H, int
  * fc.in_features fixes the accepted input H x W (in_h, in_w must be given). */
 int sfv_rbvae_create(const SfvTensor* tensors, int32_t n_tensors, int32_t in_channels,
                      int32_t in_h, int32_t in_w, SfvRbvae** out);
+/* Same with an arithmetic mode: SFV_PREC_F32 (default of sfv_rbvae_create: every layer fp32, codes
+ * bit-exact outside the |h|<1e-3 band) or BF16/FP16 (the two C->C stride-2 convolutions, 97 % of the
+ * RBVAE FLOPs, run on the tcgen05 kernel with 16-bit operands; conv.0, fc and the LSTM stay fp32). */
+int sfv_rbvae_create_ex(const SfvTensor* tensors, int32_t n_tensors, int32_t in_channels,
+                        int32_t in_h, int32_t in_w, int32_t precision, SfvRbvae** out);
 void sfv_rbvae_destroy(SfvRbvae* rb);
 int sfv_rbvae_latent_dim(const SfvRbvae* rb);
 int sfv_rbvae_workspace_bytes(const SfvRbvae* rb, int32_t N, size_t* bytes);

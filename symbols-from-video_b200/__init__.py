@@ -21,5 +21,6 @@ from .rbvae import Seq2SeqBinaryVAE, hamming_matrix, unpack_codes
 from .pipeline import (EncodeResult, FramePipeline, all_gather_ragged, encode_sharded, load_embeddings_npy,
                        lookup_embedding, save_embeddings_npy, shard_range)
 from . import ops
+from .weights import init_encoder_state_dict, init_rbvae_state_dict, synthetic_frames
 
 __all__ = [n for n in dir() if not n.startswith("_")]

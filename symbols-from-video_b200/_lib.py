@@ -63,6 +63,8 @@ SIGNATURES = {
                                              C.POINTER(C.c_size_t)]),
     "sfv_rbvae_create": (C.c_int, [C.POINTER(SfvTensor), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(_P)]),
+    "sfv_rbvae_create_ex": (C.c_int, [C.POINTER(SfvTensor), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(_P)]),
     "sfv_rbvae_destroy": (None, [_P]),
     "sfv_rbvae_latent_dim": (C.c_int, [_P]),
     "sfv_rbvae_workspace_bytes": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_size_t)]),

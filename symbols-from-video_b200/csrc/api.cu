@@ -177,13 +177,21 @@ int sfv_resize_normalise(const uint8_t* frames, int32_t B, int32_t Hs, int32_t W
 
 int sfv_rbvae_create(const SfvTensor* tensors, int32_t n_tensors, int32_t in_channels, int32_t in_h, int32_t in_w,
                      SfvRbvae** out) {
+  return sfv_rbvae_create_ex(tensors, n_tensors, in_channels, in_h, in_w, SFV_PREC_F32, out);
+}
+
+int sfv_rbvae_create_ex(const SfvTensor* tensors, int32_t n_tensors, int32_t in_channels, int32_t in_h, int32_t in_w,
+                        int32_t precision, SfvRbvae** out) {
   if (!out || !tensors) return fail(SFV_ERR_INVALID, "rbvae_create: null argument");
   *out = nullptr;
+  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16)
+    return fail(SFV_ERR_INVALID, "rbvae_create: unknown precision %d", precision);
   if (in_channels < 1 || in_h < 1 || in_w < 1) return fail(SFV_ERR_INVALID, "rbvae_create: bad input shape");
   SFV_TRY(require_device());
   SfvRbvae* r = new (std::nothrow) SfvRbvae();
   if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
   r->in_channels = in_channels; r->in_h = in_h; r->in_w = in_w;
+  r->prec = precision; r->fmt = fmt_of_precision(precision);
   int st = rbvae_build(r, tensors, n_tensors);
   if (st != 0) { r->blob.release(); delete r; return st; }
   *out = r;

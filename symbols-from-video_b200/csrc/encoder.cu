@@ -258,11 +258,12 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
 }
 
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
-             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s) {
+             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s,
+             void* out16, int fmt16) {
   IgemmArgs a;
   memset(&a, 0, sizeof(a));
   a.x = in; a.src_kind = src_kind; a.w = w.w32; a.w_sk = w.Cout; a.w_sn = 1; a.w_batch = 0;
-  a.bias = w.bias; a.residual = residual; a.y = out;
+  a.bias = w.bias; a.residual = residual; a.y = out; a.y16 = out16; a.fmt16 = fmt16;
   a.N = N; a.H = H; a.W = W; a.Cin = w.Cin; a.Cout = w.Cout;
   a.ksize = w.ks; a.stride = stride; a.pad = pad_lo;
   a.Ho = (H + pad_lo + pad_hi - w.ks) / stride + 1;

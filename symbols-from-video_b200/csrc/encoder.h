@@ -25,7 +25,8 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
             int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
             double* gn_stats = nullptr);
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
-             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s);
+             int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s,
+             void* out16 = nullptr, int fmt16 = 0);
 int attention_f32(const float* q, const float* k, const float* v, float* O, float* S, int N, int L, int C,
                   float scale, cudaStream_t s);
 int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cudaStream_t s);
@@ -36,7 +37,7 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
 }  // namespace sfv
 
 struct SfvEncoder {
-  int prec = 0, fmt = 0, chunk = 8;
+  int prec = 0, fmt = 0, chunk = 16;
   bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
   sfv::DeviceBlob blob;
   sfv::ConvW conv_in, ds[3], q, k, v, qk, proj, conv_out;
@@ -46,6 +47,7 @@ struct SfvEncoder {
 
 struct SfvRbvae {
   int in_channels = 0, in_h = 0, in_w = 0, channels = 0, layers = 0, L = 0;
+  int prec = 0, fmt = 0;              // SFV_PREC_F32: all fp32; BF16/FP16: the two C->C stride-2 convs on tcgen05
   int fh = 0, fw = 0;                 // feature map after the three stride-2 convs
   sfv::DeviceBlob blob;
   sfv::ConvW c0, c1, c2;

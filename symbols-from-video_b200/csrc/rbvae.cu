@@ -42,7 +42,8 @@ int rbvae_build(SfvRbvae* r, const SfvTensor* t, int n) {
     const SfvTensor* bb = find_t(t, n, std::string(names[i]) + ".bias");
     if (!ww || !bb || ww->shape[0] != r->channels || ww->shape[1] != cin || ww->shape[2] != 3)
       return fail(SFV_ERR_MISSING_KEY, "rbvae: missing/mis-shaped %s", names[i]);
-    SFV_TRY(make_conv_from_host(r->blob, ww->host_data, bb->host_data, r->channels, cin, 3, FMT_BF16, false, cw[i]));
+    SFV_TRY(make_conv_from_host(r->blob, ww->host_data, bb->host_data, r->channels, cin, 3, r->fmt,
+                                r->prec != SFV_PREC_F32 && i > 0, cw[i]));
     cin = r->channels;
   }
   {  // fc weight: reference flatten order is (C,H,W) (nn.Flatten on NCHW); ours is NHWC
@@ -116,10 +117,20 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
     float* a1i = a1 + (size_t)n0 * h[1] * w[1] * r->channels;
     float* a2i = a2 + (size_t)n0 * h[2] * w[2] * r->channels;
     // conv(s2,p1)+ReLU, conv(s2,p1)+ReLU, conv(s2,p1)   (dropout is identity in eval)
-    SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));
-    SFV_TRY(conv_f32(r->c1, a1i, SRC_NHWC_F32, nn, h[1], w[1], 2, 1, 1, nullptr, a2i, 1, 1.f, s));
-    // third conv output reuses a1 (dead after conv 2)
-    SFV_TRY(conv_f32(r->c2, a2i, SRC_NHWC_F32, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, 0, 1.f, s));
+    const bool tc = r->prec != SFV_PREC_F32 && r->c1.w16 && r->c2.w16 && h[1] % 2 == 0 && w[1] % 2 == 0 &&
+                    h[2] % 2 == 0 && w[2] % 2 == 0;
+    if (tc) {
+      // 16-bit operands for the two C->C convs (97 % of the RBVAE FLOPs) on the tcgen05 kernel;
+      // conv.0 (Cin = 3 or 4) stays on CUDA cores and emits the 16-bit operand directly
+      SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt));
+      SFV_TRY(conv_tc(r->c1, r->fmt, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s));
+      SFV_TRY(conv_tc(r->c2, r->fmt, a2i, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, nullptr, 0, s));
+    } else {
+      SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));
+      SFV_TRY(conv_f32(r->c1, a1i, SRC_NHWC_F32, nn, h[1], w[1], 2, 1, 1, nullptr, a2i, 1, 1.f, s));
+      // third conv output reuses a1 (dead after conv 2)
+      SFV_TRY(conv_f32(r->c2, a2i, SRC_NHWC_F32, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, 0, 1.f, s));
+    }
     SFV_TRY(launch_fc(a1i, r->fc_w, r->fc_b, logits + (size_t)n0 * r->L, nn,
                       (long long)h[3] * w[3] * r->channels, r->L, nullptr, 0, s));
   }

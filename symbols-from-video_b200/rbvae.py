@@ -56,8 +56,12 @@ class _Lstm(nn.Module):
 
 
 class Seq2SeqBinaryVAE(nn.Module):
-    def __init__(self, in_channels=3, out_channels=3, latent_dim=32, hidden_dim=32, kind=None, input_hw=None):
+    def __init__(self, in_channels=3, out_channels=3, latent_dim=32, hidden_dim=32, kind=None, input_hw=None,
+                 precision="fp32"):
         super().__init__()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self.precision = precision
         if hidden_dim != latent_dim:
             # the reference ignores hidden_dim too: EncoderRNN(latent_dim, hidden_dim=latent_dim) (:139)
             hidden_dim = latent_dim
@@ -115,7 +119,8 @@ class Seq2SeqBinaryVAE(nn.Module):
                                    f"{H}x{W} input vs fc.in_features {have}")
             table, n, keep = _lib.make_tensor_table(self.state_dict())
             h = C.c_void_p()
-            _lib.check(_lib.lib().sfv_rbvae_create(table, n, self.in_channels, H, W, C.byref(h)))
+            _lib.check(_lib.lib().sfv_rbvae_create_ex(table, n, self.in_channels, H, W,
+                                                      _lib.PRECISIONS[self.precision], C.byref(h)))
             self._handles[key] = h
         return self._handles[key]
 

@@ -272,6 +272,26 @@ def check_rbvae_golden(name):
     return out
 
 
+def check_rbvae_tensor_core(name, prec):
+    """Opt-in 16-bit mode of the two C->C RBVAE convs: h stays close, flips are counted (reported, in-band
+    flips are expected; the strict bit-exact gate applies to the default fp32 mode)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    hw = [int(v) for v in g["hw"]]
+    m32, sd = rb_from_golden(g)
+    m = sfv_b200.Seq2SeqBinaryVAE(int(g["cin"]), int(g["cin"]), int(g["L"]), int(g["L"]), kind=str(g["kind"]),
+                                  input_hw=tuple(hw), precision=prec)
+    m.load_state_dict(sd)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    z = m.encode(x, temperature=0.5, hard=True, noise_ratio=0.0).cpu().numpy()
+    _, h, _ = m.forward(x, hard=True, noise_ratio=0.0)
+    h = h.cpu().numpy()
+    o, i, n = code_flips(z, g["z_hard"], g["h"])
+    out = dict(case=name, prec=prec, h_maxabs=float(np.abs(h - g["h"]).max()), h_scale=float(np.abs(g["h"]).max()),
+               flips_outside=o, flips_inside=i, band=n, bits=int(z.size))
+    assert out["h_maxabs"] < (2e-3 if prec == "bf16" else 3e-4), out
+    return out
+
+
 def check_hamming():
     g = torch.Generator().manual_seed(0)
     a = torch.randint(-2 ** 31, 2 ** 31 - 1, (37, 4), generator=g, dtype=torch.int64).to(torch.int32)

@@ -181,3 +181,15 @@ def test_all_gather_ragged_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_product_weight_and_frame_generators_match_the_oracles():
+    """bench.py builds its models from the product's own seeded generators; the CPU-baseline / parity leg
+    feeds the same tensors to the oracle, so both generators must agree bit for bit."""
+    a, b = sfv_b200.init_encoder_state_dict(3), kl_f8.init_state_dict(3)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in b)
+    a, b = sfv_b200.init_rbvae_state_dict(4, 25, (8, 8), seed=1), orb.init_state_dict(4, 25, (8, 8), seed=1)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in b)
+    from oracle import frames
+    assert np.array_equal(sfv_b200.synthetic_frames(2, 32, 40, 9, smooth=True).numpy(),
+                          frames.synthetic_frames(2, 32, 40, 9, smooth=True))

@@ -71,6 +71,13 @@ def test_rbvae_vs_reference_golden(name):
     print(_c().check_rbvae_golden(name))
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["rbvae_percep_L25_64x64_T1", "rbvae_percep_L100_88x160_T1",
+                                  "rbvae_contrastive_L25_256x256_T1"])
+def test_rbvae_tensor_core_mode(name, prec):
+    print(_c().check_rbvae_tensor_core(name, prec))
+
+
 def test_hamming():
     _c().check_hamming()
 

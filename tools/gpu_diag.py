@@ -39,6 +39,9 @@ def plan():
     for name in ("rbvae_percep_L25_32x32_T1", "rbvae_percep_L25_64x64_T1", "rbvae_percep_L100_88x160_T1",
                  "rbvae_percep_L50_32x32_T4", "rbvae_contrastive_L25_256x256_T1"):
         items.append((f"rbvae/{name}", f"check_rbvae_golden({name!r})"))
+    for name in ("rbvae_percep_L25_64x64_T1", "rbvae_percep_L100_88x160_T1", "rbvae_contrastive_L25_256x256_T1"):
+        for prec in ("bf16", "fp16"):
+            items.append((f"rbvae_tc/{prec}/{name}", f"check_rbvae_tensor_core({name!r},{prec!r})"))
     for prec in ("fp32", "fp16", "bf16"):
         items.append((f"pipeline/{prec}", f"check_pipeline({prec!r})"))
     items.append(("fullsize/bf16", "check_full_size_properties('bf16',4,512)"))
