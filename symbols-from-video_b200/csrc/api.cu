@@ -118,6 +118,7 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
   e->prec = precision;
   e->fmt = fmt_of_precision(precision);
   if (const char* v = getenv("SFV_FUSED_STATS")) e->fused_stats = atoi(v) != 0;
+  if (const char* v = getenv("SFV_FUSE_NIN")) e->fuse_nin = atoi(v) != 0;
   int st = encoder_build(e, tensors, n_tensors);
   if (st != 0) { e->blob.release(); delete e; return st; }
   *out = e;

@@ -179,6 +179,8 @@ struct TcGemmArgs {
   const void* b; unsigned long long b_rows, b_k; unsigned long long b_row_stride, b_batch_stride;
   int b_batched;
   int ntaps; TcTap taps[9]; int tap_k[9];  // tap_k: k offset in B for this tap
+  const void* a2; int a2_cin;        // optional second A tensor [N,Ho,Wo,a2_cin] read as one extra 1x1 tap (fused shortcut)
+  int a2_k0;                         // its k offset in B
   int halo_ok;                       // 3x3 stride-1 conv whose taps are row-major with x offsets -1,0,+1
   int kchunks;                       // 64-wide K chunks per tap
   // tiling of the output

@@ -107,7 +107,31 @@ static int get_res(DeviceBlob& blob, const SfvTensor* t, int n, const std::strin
   SFV_TRY(get_norm(blob, t, n, name + ".norm2", Cout, &r->n2));
   SFV_TRY(get_conv(blob, t, n, name + ".conv2", Cout, Cout, 3, fmt, want16, &r->c2));
   r->has_nin = Cin != Cout;
-  if (r->has_nin) SFV_TRY(get_conv(blob, t, n, name + ".nin_shortcut", Cout, Cin, 1, fmt, want16, &r->nin));
+  if (r->has_nin) {
+    SFV_TRY(get_conv(blob, t, n, name + ".nin_shortcut", Cout, Cin, 1, fmt, want16, &r->nin));
+    if (want16) {
+      // conv2 and the 1x1 nin_shortcut write the same output (x + h, model.py:136-141): fold the shortcut into
+      // conv2's GEMM as Cin extra K columns  [W2 (tap-major) | Wnin],  bias b2 + bnin
+      const SfvTensor* w2 = find_tensor(t, n, name + ".conv2.weight");
+      const SfvTensor* b2 = find_tensor(t, n, name + ".conv2.bias");
+      const SfvTensor* wn = find_tensor(t, n, name + ".nin_shortcut.weight");
+      const SfvTensor* bn = find_tensor(t, n, name + ".nin_shortcut.bias");
+      const int K = 9 * Cout + Cin;
+      std::vector<uint16_t> w16((size_t)Cout * K, 0);
+      std::vector<float> bias(Cout);
+      for (int o = 0; o < Cout; ++o) {
+        for (int i = 0; i < Cout; ++i)
+          for (int tp = 0; tp < 9; ++tp)
+            w16[(size_t)o * K + (size_t)tp * Cout + i] = host_to_16(w2->host_data[((size_t)o * Cout + i) * 9 + tp], fmt);
+        for (int i = 0; i < Cin; ++i) w16[(size_t)o * K + 9 * Cout + i] = host_to_16(wn->host_data[(size_t)o * Cin + i], fmt);
+        bias[o] = b2->host_data[o] + bn->host_data[o];
+      }
+      ConvW& f = r->c2n;
+      f.Cin = Cout; f.Cout = Cout; f.ks = 3; f.cout_pad = Cout; f.extra_k = Cin;
+      SFV_TRY(blob.upload(w16.data(), w16.size() * 2, &f.w16));
+      SFV_TRY(blob.upload(bias.data(), bias.size() * 4, (void**)&f.bias));
+    }
+  }
   return 0;
 }
 
@@ -200,7 +224,7 @@ static int pick_block_n(int cout_pad) {
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
 int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats) {
+            double* gn_stats, const void* a2_16) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
@@ -244,7 +268,11 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
       }
   }
   a.kchunks = Cin / 64;
-  a.b = w.w16; a.b_rows = w.cout_pad; a.b_k = (unsigned long long)ks * ks * Cin;
+  if (w.extra_k) {
+    SFV_CHECK(a2_16 != nullptr && stride == 1 && w.extra_k % 64 == 0, "conv_tc: fused 1x1 branch needs its input tensor");
+    a.a2 = a2_16; a.a2_cin = w.extra_k; a.a2_k0 = ks * ks * Cin;
+  }
+  a.b = w.w16; a.b_rows = w.cout_pad; a.b_k = (unsigned long long)ks * ks * Cin + w.extra_k;
   a.b_row_stride = a.b_k * 2; a.b_batched = 0;
   a.Wo = Wo; a.Ho = Ho; a.Nimg = N; a.Cout = w.Cout;
   a.block_n = pick_block_n(w.cout_pad);
@@ -341,11 +369,17 @@ struct Fwd {
     SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
     SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
     const float* res = x;
+    void* copy = (tc && want_copy) ? pl.x16 : nullptr;
+    if (r.has_nin && tc && e->fuse_nin) {
+      // x' = nin(x) + conv2(a2): one GEMM, the 1x1 shortcut rides along as extra K chunks read from x's 16-bit copy
+      SFV_TRY(conv_tc(r.c2n, fmt, pl.oa, N, H, W, 1, 1, 1, nullptr, xo, copy, 0, s, sx(), x_op));
+      *xo_op = copy;
+      return 0;
+    }
     if (r.has_nin) {
       SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr, nullptr));
       res = xo;
     }
-    void* copy = (tc && want_copy) ? pl.x16 : nullptr;
     SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy, sx()));
     *xo_op = tc ? copy : (const void*)xo;
     return 0;

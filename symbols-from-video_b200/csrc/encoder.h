@@ -12,18 +12,19 @@ struct DeviceBlob {
 
 struct ConvW {
   int Cin = 0, Cout = 0, ks = 0, cout_pad = 0;
+  int extra_k = 0;         // channels of a fused 1x1 branch appended to K (nin_shortcut folded into conv2)
   float* w32 = nullptr;    // [ks*ks*Cin][Cout] fp32 (CUDA-core kernel)
   void* w16 = nullptr;     // [cout_pad][ks*ks*Cin] 16-bit, K-major (UMMA B operand)
   float* bias = nullptr;   // [cout_pad]
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
-struct ResW { NormW n1, n2; ConvW c1, c2, nin; bool has_nin = false; };
+struct ResW { NormW n1, n2; ConvW c1, c2, nin, c2n; bool has_nin = false; };   // c2n: conv2 with nin_shortcut fused along K
 
 int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
                         int fmt, bool want16, ConvW* out);
 int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats = nullptr);
+            double* gn_stats = nullptr, const void* a2_16 = nullptr);
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
              int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s,
              void* out16 = nullptr, int fmt16 = 0);
@@ -38,6 +39,7 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
 
 struct SfvEncoder {
   int prec = 0, fmt = 0, chunk = 16;
+  bool fuse_nin = true;        // nin_shortcut folded into conv2's GEMM (tensor-core modes)
   bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
   sfv::DeviceBlob blob;
   sfv::ConvW conv_in, ds[3], q, k, v, qk, proj, conv_out;

@@ -51,6 +51,7 @@ struct TcParams {
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
   int epi_mode;
   int halo_base_offset;
+  int a2_kchunks, a2_k0;               // fused 1x1 branch: extra k-chunks read through the second A map
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
 };
@@ -377,7 +378,7 @@ struct Cfg {
 template <int BLOCK_N, int NCTA, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
                const __grid_constant__ CUtensorMap tmO16, const TcParams p) {
   using C = Cfg<BLOCK_N, NCTA, HALO>;
   // NCTA == 2: the kernel runs as clusters of two CTAs (one SM pair) that share one
@@ -426,7 +427,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (NCTA == 2) cluster_sync_all();     // peer barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int k_iters = (p.ntaps / C::kGroup) * p.kchunks;
+  const int k_iters = (p.ntaps / C::kGroup) * p.kchunks + p.a2_kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
@@ -472,6 +473,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int g = 0; g < C::kGroup; ++g)
                   tma_load_3d(sa + C::kABytes + g * C::kBBytes, &tmB, fb, p.tap_k[tap + g] + kc * kBlockK,
                               n_tile * BLOCK_N, p.b_batched ? img : 0);
+              }
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if constexpr (!HALO) {
+          // fused 1x1 branch (nin_shortcut): same pixels, no tap shift, channels of the second tensor
+          for (int kc = 0; kc < p.a2_kchunks && ok; ++kc) {
+            ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
+            if (!ok) break;
+            const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (elect_one_sync()) {
+              if constexpr (NCTA == 2) {
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kTxBytes);
+                tma_load_5d_2cta(sa, &tmA2, fb, kc * kBlockK, base[1], base[2], base[3], base[4]);
+                tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK,
+                                 n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), 0);
+              } else {
+                mbar_arrive_expect_tx(fb, C::kTxBytes);
+                tma_load_5d(sa, &tmA2, fb, kc * kBlockK, base[1], base[2], base[3], base[4]);
+                tma_load_3d(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK, n_tile * BLOCK_N, 0);
               }
             }
             __syncwarp();
@@ -860,7 +884,7 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
 }
 
 template <int BLOCK_N, int NCTA, bool HALO = false>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo32,
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mr, const CUtensorMap& mo32,
                const CUtensorMap& mo16, const TcParams& p, cudaStream_t s, const char* tag) {
   using C = Cfg<BLOCK_N, NCTA, HALO>;
   static bool attr_set = false;
@@ -881,7 +905,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 8 * 256, s));
-  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO>, ma, mb, mr, mo32, mo16, p));
+  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO>, ma, mb, ma2, mr, mo32, mo16, p));
   SFV_LAUNCH_OK();
   if (g_dbg) {
     std::vector<unsigned long long> h(8 * 256);
@@ -905,7 +929,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_CHECK(a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0");
   SFV_CHECK(a.block_n <= 256, "tc_gemm: block_n > 256");
   SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma2;
   // HALO variant: 3x3 stride-1 conv, 128-pixel row-segment tiles, taps ordered row-major with dx = -1,0,+1
   const bool halo = g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
                     a.block_n == 128 && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
@@ -917,8 +941,17 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
       box[i] = i < a.a_rank ? a.a_box[i] : 1;
     }
     if (halo) box[a.dim_x] = 130;
+    if (a.a2) {   // same geometry as A, different channel count
+      SFV_CHECK(!halo && a.a_rank == 4 && a.a2_cin % 64 == 0, "tc_gemm: fused 1x1 branch needs a plain NHWC stride-1 A tensor");
+      cuuint64_t d2[5], s2[5];
+      for (int i = 0; i < 5; ++i) { d2[i] = dims[i]; s2[i] = strides[i]; }
+      d2[0] = a.a2_cin;
+      s2[1] = (cuuint64_t)a.a2_cin * 2; s2[2] = s2[1] * d2[1]; s2[3] = s2[2] * d2[2]; s2[4] = s2[3] * d2[3];
+      SFV_TRY(encode_map(&ma2, a.fmt, 5, a.a2, d2, s2, box));
+    }
     strides[0] = 2;
     SFV_TRY(encode_map(&ma, a.fmt, 5, a.a, dims, strides, box));
+    if (!a.a2) ma2 = ma;
   }
   // CTA pairs (cta_group::2): two adjacent 128-pixel tiles share one B tile, halving the shared-memory
   // operand traffic per MMA.  A batched B (attention) must be the same for both tiles of a pair.
@@ -949,6 +982,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
   p.epi_mode = g_epi_mode;
   p.dbg = g_dbg;
+  p.a2_kchunks = a.a2 ? a.a2_cin / 64 : 0; p.a2_k0 = a.a2_k0;
   p.halo_base_offset = g_halo_boff;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
@@ -979,22 +1013,22 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
-  if (halo) return launch_cfg<128, 2, true>(ma, mb, mr, mo32, mo16, p, s, tag);
+  if (halo) return launch_cfg<128, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
   if (ncta == 2) {
     switch (a.block_n) {
-      case 256: return launch_cfg<256, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
-      case 128: return launch_cfg<128, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
-      case 64: return launch_cfg<64, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
-      case 32: return launch_cfg<32, 2>(ma, mb, mr, mo32, mo16, p, s, tag);
+      case 256: return launch_cfg<256, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+      case 128: return launch_cfg<128, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+      case 64: return launch_cfg<64, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+      case 32: return launch_cfg<32, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
       default: break;
     }
   }
   switch (a.block_n) {
-    case 256: return launch_cfg<256, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
-    case 128: return launch_cfg<128, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
-    case 64: return launch_cfg<64, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
-    case 32: return launch_cfg<32, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
-    case 16: return launch_cfg<16, 1>(ma, mb, mr, mo32, mo16, p, s, tag);
+    case 256: return launch_cfg<256, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+    case 128: return launch_cfg<128, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+    case 64: return launch_cfg<64, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+    case 32: return launch_cfg<32, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+    case 16: return launch_cfg<16, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
     default: return fail(SFV_ERR_INVALID, "tc_gemm: unsupported block_n %d", a.block_n);
   }
 }
