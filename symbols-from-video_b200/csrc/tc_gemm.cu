@@ -372,7 +372,7 @@ struct Cfg {
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kAuxBytes + 1024 /*align slack*/;
-  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kStages >= (HALO ? 2 : 3), "pipeline too shallow");   // a HALO stage carries 12 MMAs
 };
 
 template <int BLOCK_N, int NCTA, bool HALO>
@@ -479,8 +479,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
-        if constexpr (!HALO) {
+        {
           // fused 1x1 branch (nin_shortcut): same pixels, no tap shift, channels of the second tensor
+          // (one plain 128-pixel A box + one B tile per stage, also inside a HALO kernel)
+          constexpr int kTx1 = kBlockM * kBlockK * 2 + C::kBBytes;
           for (int kc = 0; kc < p.a2_kchunks && ok; ++kc) {
             ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
             if (!ok) break;
@@ -488,12 +490,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (elect_one_sync()) {
               if constexpr (NCTA == 2) {
-                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kTxBytes);
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * kTx1);
                 tma_load_5d_2cta(sa, &tmA2, fb, kc * kBlockK, base[1], base[2], base[3], base[4]);
                 tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK,
                                  n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), 0);
               } else {
-                mbar_arrive_expect_tx(fb, C::kTxBytes);
+                mbar_arrive_expect_tx(fb, kTx1);
                 tma_load_5d(sa, &tmA2, fb, kc * kBlockK, base[1], base[2], base[3], base[4]);
                 tma_load_3d(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK, n_tile * BLOCK_N, 0);
               }
@@ -527,9 +529,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const int main_iters = k_iters - p.a2_kchunks;
           if (elect_one_sync()) {
 #pragma unroll
             for (int g = 0; g < C::kGroup; ++g) {
+              if (g > 0 && it >= main_iters) break;      // fused 1x1 branch stages carry a single tap
               // HALO: tap g of the filter row reads the same box one pixel (128 B) further right.  The 128B swizzle
               // is applied to absolute smem address bits by both TMA and UMMA, so a start address that is
               // 128-byte (not 1024-byte) aligned needs no descriptor base offset (verified on B200).
@@ -837,7 +841,7 @@ EncodeTiledFn g_encode = nullptr;
 int* g_err_flag = nullptr;
 int g_num_sms = 0;
 int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
-int g_halo = 1;         // SFV_HALO=0 disables the shared A halo box
+int g_halo = 2;         // SFV_HALO=0 disables the shared A halo box; 2 also uses it for BLOCK_N = 256 (2-stage pipeline)
 int g_halo_boff = 0;    // descriptor base-offset for the shifted taps: measured WRONG on B200 (the swizzle is a function of
                         // the absolute smem address bits), so it stays 0; SFV_HALO_BOFF=1 reproduces the failing variant
 int g_epi_mode = 1;
@@ -932,7 +936,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   CUtensorMap ma, mb, ma2;
   // HALO variant: 3x3 stride-1 conv, 128-pixel row-segment tiles, taps ordered row-major with dx = -1,0,+1
   const bool halo = g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
-                    a.block_n == 128 && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
+                    (a.block_n == 128 || (a.block_n == 256 && g_halo >= 2)) && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
   {
     cuuint64_t dims[5], strides[5]; cuuint32_t box[5];
     for (int i = 0; i < 5; ++i) {
@@ -940,15 +944,15 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
       strides[i] = i < a.a_rank ? a.a_strides[i] : (i > 0 ? strides[i - 1] * dims[i - 1] : 2);
       box[i] = i < a.a_rank ? a.a_box[i] : 1;
     }
-    if (halo) box[a.dim_x] = 130;
     if (a.a2) {   // same geometry as A, different channel count
-      SFV_CHECK(!halo && a.a_rank == 4 && a.a2_cin % 64 == 0, "tc_gemm: fused 1x1 branch needs a plain NHWC stride-1 A tensor");
+      SFV_CHECK(a.a_rank == 4 && a.a2_cin % 64 == 0, "tc_gemm: fused 1x1 branch needs a plain NHWC stride-1 A tensor");
       cuuint64_t d2[5], s2[5];
       for (int i = 0; i < 5; ++i) { d2[i] = dims[i]; s2[i] = strides[i]; }
       d2[0] = a.a2_cin;
       s2[1] = (cuuint64_t)a.a2_cin * 2; s2[2] = s2[1] * d2[1]; s2[3] = s2[2] * d2[2]; s2[4] = s2[3] * d2[3];
       SFV_TRY(encode_map(&ma2, a.fmt, 5, a.a2, d2, s2, box));
     }
+    if (halo) box[a.dim_x] = 130;
     strides[0] = 2;
     SFV_TRY(encode_map(&ma, a.fmt, 5, a.a, dims, strides, box));
     if (!a.a2) ma2 = ma;
@@ -1013,6 +1017,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
+  if (halo && a.block_n == 256) return launch_cfg<256, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
   if (halo) return launch_cfg<128, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
   if (ncta == 2) {
     switch (a.block_n) {

@@ -348,3 +348,108 @@ def check_full_size_properties(prec="bf16", B=4, R=512):
     assert out["deterministic"] or rel_l2(a, b) < 1e-6, out
     assert out["perm_rel"] < 1e-6 and out["finite"], out
     return out
+
+
+def check_native_frame_size(prec="fp16"):
+    """The reference's native frame size 1280x704 (get_percep_embeddings.py:60-66): non-square, W not a
+    power of two, 14080 attention tokens; one frame against the CPU oracle (about 15 s of CPU)."""
+    vae, sd = make_vae(prec, 0)
+    u8 = frames.synthetic_frames(1, 704, 1280, 77, smooth=True)
+    x = frames.normalise_u8(u8)
+    post = vae.encode_uint8(torch.from_numpy(u8).to(DEV))
+    vae.check_async_error()
+    ref = kl_f8.encode(x, sd)
+    out = dict(prec=prec, mean=rel_l2(post.mean, ref.mean), logvar=rel_l2(post.logvar, ref.logvar),
+               shape=list(post.mean.shape))
+    assert out["shape"] == [1, 4, 88, 160]
+    assert out["mean"] <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), out
+    # native RBVAE shape (fc = 256*11*20) on the resulting latent
+    rsd = orb.init_state_dict(4, 25, (11, 20), seed=3)
+    rb = sfv_b200.Seq2SeqBinaryVAE(in_channels=4, out_channels=4, latent_dim=25, hidden_dim=25)   # reference defaults
+    rb.load_state_dict(rsd)
+    lat = sfv_b200.FirstStage(vae).get_first_stage_mode(post)
+    z = rb.encode(lat[:, None], hard=True, noise_ratio=0.0).cpu().numpy()
+    z_ref, h_ref = orb.encode(kl_f8.first_stage_encoding(ref, use_mode=True)[:, None], rsd, hard=True, noise_ratio=0.0,
+                              return_h=True)
+    o, i, n = code_flips(z, z_ref.numpy(), h_ref.numpy())
+    out.update(flips_outside=o, flips_inside=i, band=n)
+    return out
+
+
+def check_large_frame_properties(prec="bf16", R=1024, B=2):
+    """BASELINE config 5 frame size (4x128x128 latent, 16384-token mid attention): too slow for the CPU
+    oracle, so size-independent properties only -- finite, deterministic, batch-permutation equivariant,
+    and equal to the same frames pushed one at a time (chunking / attention sub-chunking)."""
+    vae, sd = make_vae(prec, 0)
+    u8 = torch.from_numpy(frames.synthetic_frames(B, R, R, 21, smooth=True)).to(DEV)
+    a = vae.encode_uint8(u8).parameters.clone()
+    b = torch.cat([vae.encode_uint8(u8[i:i + 1]).parameters for i in range(B)])
+    c = vae.encode_uint8(u8.flip(0).contiguous()).parameters.flip(0)
+    vae.check_async_error()
+    out = dict(finite=bool(torch.isfinite(a).all()), single_vs_batch=rel_l2(b, a), flip_equivariance=rel_l2(c, a),
+               mean_std=float(a[:, :4].std()), shape=list(a.shape))
+    assert out["finite"] and out["single_vs_batch"] < 1e-6 and out["flip_equivariance"] < 1e-6, out
+    assert out["shape"] == [B, 8, R // 8, R // 8]
+    return out
+
+
+def check_contrastive_512(prec="fp32"):
+    """BASELINE config 4: contrastive (pixel-space) RBVAE encoder on 512x512 frames in [0,1]; fc = 64*64*64."""
+    L = 32
+    rsd = orb.init_state_dict(3, L, (64, 64), channels=64, num_layers=2, seed=8)
+    rb = sfv_b200.Seq2SeqBinaryVAE(in_channels=3, out_channels=3, latent_dim=L, hidden_dim=L, input_hw=(512, 512),
+                                   precision=prec)
+    rb.load_state_dict(rsd)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 2, 3, 512, 512, generator=g)          # pairs: [B, T=2, C, H, W]
+    z, h = orb.encode(x, rsd, hard=True, noise_ratio=0.0, return_h=True)
+    codes, hh = rb.encode_codes(x.to(DEV))
+    zz = sfv_b200.unpack_codes(codes, L).cpu().numpy().reshape(2, 2, L)
+    o, i, n = code_flips(zz, z.numpy(), h.numpy())
+    out = dict(prec=prec, h_maxabs=float((hh.cpu() - h).abs().max()), flips_outside=o, flips_inside=i, band=n,
+               bits=int(zz.size))
+    assert out["h_maxabs"] < (2e-5 if prec == "fp32" else 2e-3), out
+    if prec == "fp32":
+        assert o == 0, out
+    return out
+
+
+def check_edge_cases():
+    """Empty / minimal / ragged inputs and error behaviour at the boundary."""
+    import pytest
+    vae, sd = make_vae("bf16", 0)
+    out = {}
+    # smallest legal frame (8x8 -> 1x1 latent) is refused by the tensor-core attention (L % 8) but fine in fp32
+    with pytest.raises(sfv_b200.SfvError):
+        vae.encode(torch.zeros(1, 3, 8, 8, device=DEV))
+    v32, _ = make_vae("fp32", 0)
+    p = v32.encode(torch.zeros(1, 3, 8, 8, device=DEV))
+    ref = kl_f8.encode(torch.zeros(1, 3, 8, 8), sd)
+    out["tiny_8x8_fp32"] = rel_l2(p.mean, ref.mean)
+    assert out["tiny_8x8_fp32"] < 1e-4
+    # H, W not multiples of 8 -> ValueError like any shape error; wrong channel count too
+    for bad in (torch.zeros(1, 3, 60, 64, device=DEV), torch.zeros(1, 4, 64, 64, device=DEV)):
+        with pytest.raises(ValueError):
+            vae.encode(bad)
+    # ragged batch sizes around the chunk size (chunk 16): 1, 15, 17 frames give the same per-frame result
+    x = frames.normalise_u8(frames.synthetic_frames(17, 32, 64, 3)).to(DEV)
+    full = vae.encode(x).parameters
+    out["b1_vs_b17"] = rel_l2(vae.encode(x[:1]).parameters, full[:1])
+    out["b15_vs_b17"] = rel_l2(vae.encode(x[:15]).parameters, full[:15])
+    assert out["b1_vs_b17"] < 1e-6 and out["b15_vs_b17"] < 1e-6, out
+    # pipeline with an empty frame list
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, input_hw=(4, 8))
+    rb.load_state_dict(orb.init_state_dict(4, 25, (1, 1), seed=0))
+    res = sfv_b200.FramePipeline(vae, rb, batch=4).encode_host(torch.zeros(0, 32, 64, 3, dtype=torch.uint8))
+    assert res.latents is None and res.codes is None
+    # noise_ratio != 0 without draws is handled by the mirror (global RNG); the raw ABI refuses it
+    import ctypes as C
+    h = rb._native(4, 8)
+    lat = torch.zeros(1, 1, 4, 4, 8, device=DEV)
+    nb = C.c_size_t(); sfv_b200.lib().sfv_rbvae_workspace_bytes(h, 1, C.byref(nb))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    hb = torch.empty(1, 25, device=DEV)
+    st = sfv_b200.lib().sfv_rbvae_encode(h, lat.data_ptr(), 1, 1, 1.0, None, 0.3, 0.5, 1, hb.data_ptr(), None, None,
+                                         ws.data_ptr(), nb.value, None)
+    assert st == -1 and b"uniform draws" in sfv_b200.lib().sfv_last_error()
+    return out

@@ -89,3 +89,21 @@ def test_pipeline_frames_to_codes(prec):
 
 def test_full_size_properties_512():
     print(_c().check_full_size_properties("bf16", B=4, R=512))
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_native_1280x704_frame(prec):
+    print(_c().check_native_frame_size(prec))
+
+
+def test_large_frame_properties_1024():
+    print(_c().check_large_frame_properties("bf16", 1024, 2))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_contrastive_rbvae_512(prec):
+    print(_c().check_contrastive_512(prec))
+
+
+def test_edge_cases_and_errors():
+    print(_c().check_edge_cases())

@@ -45,6 +45,10 @@ def plan():
     for prec in ("fp32", "fp16", "bf16"):
         items.append((f"pipeline/{prec}", f"check_pipeline({prec!r})"))
     items.append(("fullsize/bf16", "check_full_size_properties('bf16',4,512)"))
+    items += [("native/fp16", "check_native_frame_size('fp16')"), ("native/bf16", "check_native_frame_size('bf16')"),
+              ("large1024/bf16", "check_large_frame_properties('bf16',1024,2)"),
+              ("contrastive512/fp32", "check_contrastive_512('fp32')"), ("contrastive512/bf16", "check_contrastive_512('bf16')"),
+              ("edge", "check_edge_cases()")]
     return items
 
 
