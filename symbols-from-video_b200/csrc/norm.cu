@@ -264,6 +264,22 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, void*
   }
 }
 
+// any row length (tiny latents in check mode): one warp per row, scalar accesses
+__global__ void softmax_rows_scalar_kernel(const float* x, float* y, long long rows, int cols) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + r * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += expf(xr[c] - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  for (int c = lane; c < cols; c += 32) y[r * cols + c] = expf(xr[c] - mx) * inv;
+}
+
 // DiagonalGaussian head (distributions.py:24-31): moments NHWC [N,HW,8] ->
 //   parameters NCHW [N,8,HW] (raw; mean = channels 0..3), logvar = clamp(ch 4..7, -30, 20),
 //   std = exp(0.5 logvar), var = exp(logvar)   (each NCHW [N,4,HW]; std/var optional)
@@ -363,8 +379,13 @@ int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t
 
 int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,
                         cudaStream_t s) {
-  SFV_CHECK(cols % 4 == 0, "softmax: cols %% 4 != 0");
   SFV_CHECK(rows < (1ll << 31), "softmax: too many rows");
+  if (cols % 4 != 0) {
+    SFV_CHECK(!y_is16, "softmax: 16-bit output needs cols %% 4 == 0");
+    softmax_rows_scalar_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, (float*)y, rows, cols);
+    SFV_LAUNCH_OK();
+    return 0;
+  }
   ProfScope prof(PROF_SOFTMAX, (double)rows * cols * (4 + (y_is16 ? 2 : 4)), s);
   if (y_is16) softmax_rows_kernel<true><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
   else softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, s>>>(x, y, fmt, cols);
