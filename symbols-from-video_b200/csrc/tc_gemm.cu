@@ -17,8 +17,8 @@
 //   ReLU, then write fp32 and/or 16-bit NHWC rows (and optional GroupNorm
 //   partial sums for the consumer's normalisation).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
-// allocator, warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
+// allocator, warps 2.. = epilogue (4 or 8 warps; TMEM lane quarter = warp_idx % 4).
 #include "common.cuh"
 #include <cuda.h>
 
@@ -28,7 +28,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 x 16-bit = 128 B = one swizzle row
-constexpr int kThreads = 192;
 constexpr unsigned long long kWatchdogCycles = 4000000000ull;  // ~2 s
 
 struct TcParams {
@@ -349,9 +348,9 @@ __device__ __forceinline__ void epi_stats_chunk(const float* f, bool valid, int 
 // Epilogue staging (per epilogue warp): a ring of kResBufs fp32 tiles (32 rows x 128 B, 128B-swizzled) that
 // first receive the residual by TMA and then hold the fp32 output for the TMA store, and two 16-bit
 // output tiles (32 rows x 64 B, 64B-swizzled).
-constexpr int kResBufs = 3;
-constexpr int kEpiF32Bytes = 4 * kResBufs * 4096;
-constexpr int kEpiH16Bytes = 4 * 2 * 2048;
+// The epilogue of a 128 x 128 tile costs about as many cycles as its 72 MMAs when four single warps do it
+// (latency-bound instruction stream), so BLOCK_N = 128 kernels run TWO warps per TMEM lane quarter, each
+// taking half of the columns (kSets = 2, 8 epilogue warps, 2-slot rings); wider tiles keep 4 warps.
 constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias copies*/;
 
 // HALO: for 3x3 stride-1 convolutions tiled as 128-pixel row segments, one TMA box of 130 pixels feeds the
@@ -366,6 +365,12 @@ struct Cfg {
   static constexpr int kBBytes = (BLOCK_N / NCTA) * kBlockK * 2;      // a CTA pair splits B's rows
   static constexpr int kStageBytes = kABytes + kGroup * kBBytes;
   static constexpr int kTxBytes = kATxBytes + kGroup * kBBytes;
+  static constexpr int kSets = BLOCK_N == 128 ? 2 : 1;               // epilogue warps per TMEM lane quarter
+  static constexpr int kEpiWarps = 4 * kSets;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kResBufs = kSets == 2 ? 2 : 3;                // fp32 staging ring slots per warp
+  static constexpr int kEpiF32Bytes = kEpiWarps * kResBufs * 4096;
+  static constexpr int kEpiH16Bytes = kEpiWarps * 2 * 2048;
   static constexpr int kEpiBytes = BLOCK_N >= 32 ? (kEpiF32Bytes + kEpiH16Bytes) : 0;
   static constexpr int kBudget = 232448 - 1024 - kAuxBytes - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -376,7 +381,7 @@ struct Cfg {
 };
 
 template <int BLOCK_N, int NCTA, bool HALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<BLOCK_N, NCTA, HALO>::kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
                const __grid_constant__ CUtensorMap tmO16, const TcParams p) {
@@ -389,17 +394,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // SWIZZLE_128B atoms must start on 1024-byte boundaries
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_f32 = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are)
-  uint8_t* epi_h16 = epi_f32 + (C::kEpiBytes ? kEpiF32Bytes : 0);
+  uint8_t* epi_h16 = epi_f32 + (C::kEpiBytes ? C::kEpiF32Bytes : 0);
+  constexpr int kResBufs = C::kResBufs;
   uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes + C::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
-  uint64_t* res_bar = bars + 2 * C::kStages + 4;                           // [4 warps][kResBufs]
-  uint32_t* tmem_ptr = (uint32_t*)(res_bar + 4 * kResBufs);
+  uint64_t* res_bar = bars + 2 * C::kStages + 4;                           // [epilogue warps][kResBufs]
+  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * kResBufs);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
-  float* gn_acc = (float*)((uint8_t*)bars + 512);        // [4 epilogue warps][64 groups][2]
-  float* bias_all = gn_acc + 512;                        // [4 epilogue warps][256]
+  float* gn_acc = (float*)((uint8_t*)bars + 512);        // [epilogue warps][512 / warps floats]: (sum, sumsq) per group
+  float* bias_all = gn_acc + 512;                        // [epilogue warps][1024 / warps floats]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -411,13 +417,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4 * NCTA);
+      mbar_init(smem_u32(&tempty_bar[i]), C::kEpiWarps * NCTA);
     }
-    for (int i = 0; i < 4 * kResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    for (int i = 0; i < C::kEpiWarps * kResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     *abort_flag = 0;
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 512; i += kThreads) gn_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += C::kThreads) gn_acc[i] = 0.f;
   if (warp == 1) {
     if constexpr (NCTA == 2) tmem_alloc_2cta(smem_u32(tmem_ptr), C::kTmemCols);
     else tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
@@ -505,7 +511,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 1] = t_wait; }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, one elected lane issues; leader CTA only in pair mode) =====
@@ -562,25 +568,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 3] = t_full; p.dbg[blockIdx.x * 8 + 4] = t_tempty; }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 2] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 3] = t_full; p.dbg[blockIdx.x * 16 + 4] = t_tempty; }
     }
   } else {
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
     const int quarter = warp & 3;
+    const int eset = (warp - 2) >> 2;                     // which half of the columns (kSets == 2), else 0
+    const int ew = eset * 4 + quarter;                    // epilogue warp slot for the per-warp smem regions
+    constexpr int kColsPerSet = BLOCK_N / C::kSets;
+    const int cbase = eset * kColsPerSet;                 // first column of this warp inside the tile
     const int row = quarter * 32 + lane;
     const int yy = row >> p.BW_log2;
     const int xx = row & (p.BW - 1);
     // origin of this warp's 32 rows inside the tile (always a bx x by pixel rectangle, bx = min(BW, 32))
     const int wx = (quarter * 32) & (p.BW - 1), wy = (quarter * 32) >> p.BW_log2;
-    float* acc_w = gn_acc + quarter * 128;
-    float* bias_w = bias_all + quarter * 256;
+    float* acc_w = gn_acc + ew * (512 / C::kEpiWarps);
+    float* bias_w = bias_all + ew * (1024 / C::kEpiWarps);
     int gn_img = -1, gn_nt = 0;
     // GroupNorm partials are kept per warp in shared memory across the tiles of one image and
     // flushed with fp64 global atomics when the (image, n_tile) key changes.
     auto gn_flush = [&]() {
       __syncwarp();
-      const int ng2 = 2 * (BLOCK_N / p.gn_cpg);
-      const int g0 = gn_nt * BLOCK_N / p.gn_cpg;
+      const int ng2 = 2 * (kColsPerSet / p.gn_cpg);
+      const int g0 = (gn_nt * BLOCK_N + cbase) / p.gn_cpg;
       for (int t = lane; t < ng2; t += 32) {
         const float val = acc_w[t];
         acc_w[t] = 0.f;
@@ -594,8 +604,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto load_bias = [&](int n_tile) {      // per-warp shared copy: L1 is ~empty with this much smem carved out
       if (n_tile == bias_nt) return;
       __syncwarp();
-      for (int j = lane; j < BLOCK_N; j += 32) {
-        const int c = n_tile * BLOCK_N + j;
+      for (int j = lane; j < kColsPerSet; j += 32) {
+        const int c = n_tile * BLOCK_N + cbase + j;
         bias_w[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
       }
       bias_nt = n_tile;
@@ -604,20 +614,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
     unsigned long long t_tfull = 0, t_start = clock64();
-    constexpr int kNChunk = BLOCK_N / C::kChunk;
+    unsigned long long t_e[4] = {0, 0, 0, 0};   // debug: residual wait | tmem wait | math+stats+staging | store issue+wait
+    constexpr int kNChunk = kColsPerSet / C::kChunk;      // chunks of 32 columns this warp handles per tile
     const bool use_tma = C::kChunk == 32 && p.epi_mode == 1;
     const bool has_res = p.residual != nullptr;
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
-    uint8_t* f32_w = epi_f32 + quarter * (kResBufs * 4096);
-    uint8_t* h16_w = epi_h16 + quarter * (2 * 2048);
-    uint64_t* res_bar_w = res_bar + quarter * kResBufs;
+    uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
+    uint8_t* h16_w = epi_h16 + ew * (2 * 2048);
+    uint64_t* res_bar_w = res_bar + ew * kResBufs;
     auto issue_residual = [&](int g) {      // whole warp calls; one elected lane issues
       const int seq = g / kNChunk, c = g - seq * kNChunk;
       const int unit = unit0 + seq * unit_step;
       if (unit >= p.n_units) return;
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
-      const int col0 = n_tile * BLOCK_N + c * 32;
+      const int col0 = n_tile * BLOCK_N + cbase + c * 32;
       if (m_tile >= p.n_tiles_m || col0 >= p.Cout) return;     // consumer skips the same chunks
       const int tx = m_tile % p.tiles_x;
       const int ty = (m_tile / p.tiles_x) % p.tiles_y;
@@ -664,14 +675,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int sw16 = (lane >> 1) & 3;        // 64B swizzle:  chunk j of row r lives at j ^ ((r >> 1) & 3)
 #pragma unroll 1
           for (int c = 0; c < kNChunk; ++c, ++g_cur) {
-            const int c0 = c * 32;
-            const int col0 = n_tile * BLOCK_N + c0;
+            const int c0 = c * 32;                              // column inside this warp's share
+            const int col0 = n_tile * BLOCK_N + cbase + c0;
             const bool chunk_ok = tile_ok && col0 < p.Cout;     // warp-uniform
             uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
+            tmem_ld32(t_row + cbase + c0, v);
             const int slot = g_cur % kResBufs;
             uint8_t* fb = f32_w + slot * 4096 + lane * 128;
             float f[32];
+            unsigned long long tq = p.dbg ? clock64() : 0;
             if (has_res && chunk_ok) {
               ok = mbar_wait(smem_u32(&res_bar_w[slot]), (uint32_t)((g_cur / kResBufs) & 1), abort_flag, p.err, 5);
               if (!ok) break;
@@ -684,7 +696,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = 0.f;
             }
+            if (p.dbg) { const unsigned long long t1 = clock64(); t_e[0] += t1 - tq; tq = t1; }
             tmem_ld_wait();
+            if (p.dbg) { const unsigned long long t1 = clock64(); t_e[1] += t1 - tq; tq = t1; }
             if (chunk_ok) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -721,6 +735,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               fence_proxy_async();
               __syncwarp();
+              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
               if (elect_one_sync()) {
                 const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
                 if (p.out_f32) tma_store_4d(&tmO32, smem_u32(f32_w + slot * 4096), col0, ox, oy, img);
@@ -729,6 +744,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
               }
               __syncwarp();
+              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[3] += t1 - tq; tq = t1; }
             }
             if (has_res) {
               if (!chunk_ok) {                 // skipped chunk: still make sure the slot about to be refilled is free
@@ -742,11 +758,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           // reference epilogue: every lane writes its own pixel row straight from registers
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            const int col0 = n_tile * BLOCK_N + c0;
+          for (int c0 = 0; c0 < kColsPerSet; c0 += 32) {
+            const int col0 = n_tile * BLOCK_N + cbase + c0;
             if (col0 >= p.Cout) break;
             uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
+            tmem_ld32(t_row + cbase + c0, v);
             tmem_ld_wait();
             float f[32];
 #pragma unroll
@@ -818,7 +834,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     }
     if (p.gn_stats && gn_img >= 0) gn_flush();
-    if (p.dbg && warp == 2 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 6] = t_tfull; }
+    if (p.dbg && warp == 2 && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 5] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 6] = t_tfull;
+      p.dbg[blockIdx.x * 16 + 7] = t_e[0]; p.dbg[blockIdx.x * 16 + 8] = t_e[1]; p.dbg[blockIdx.x * 16 + 9] = t_e[2]; p.dbg[blockIdx.x * 16 + 10] = t_e[3];
+    }
   }
 
   tc_fence_before();
@@ -863,7 +882,7 @@ int tc_init() {
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
   if (const char* e = getenv("SFV_HALO")) g_halo = atoi(e);
   if (const char* e = getenv("SFV_HALO_BOFF")) g_halo_boff = atoi(e);
-  if (const char* e = getenv("SFV_TC_DEBUG")) { if (atoi(e)) SFV_CUDA(cudaMalloc(&g_dbg, 8 * 8 * 256)); }
+  if (const char* e = getenv("SFV_TC_DEBUG")) { if (atoi(e)) SFV_CUDA(cudaMalloc(&g_dbg, 8 * 16 * 256)); }
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
@@ -903,23 +922,23 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
   ProfScope prof(PROF_TC_GEMM, flops, s, tag);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 8 * 256, s));
+  if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 16 * 256, s));
   SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO>, ma, mb, ma2, mr, mo32, mo16, p));
   SFV_LAUNCH_OK();
   if (g_dbg) {
-    std::vector<unsigned long long> h(8 * 256);
+    std::vector<unsigned long long> h(16 * 256);
     SFV_CUDA(cudaStreamSynchronize(s));
-    SFV_CUDA(cudaMemcpy(h.data(), g_dbg, 8 * 8 * 256, cudaMemcpyDeviceToHost));
-    double a[8] = {0}; int n = 0;
-    for (int b = 0; b < grid; b += NCTA) { for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 8 + k]; ++n; }
-    for (int k = 0; k < 8; ++k) a[k] /= n;
-    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f\n",
-            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+    SFV_CUDA(cudaMemcpy(h.data(), g_dbg, 8 * 16 * 256, cudaMemcpyDeviceToHost));
+    double a[16] = {0}; int n = 0;
+    for (int b = 0; b < grid; b += NCTA) { for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k]; ++n; }
+    for (int k = 0; k < 16; ++k) a[k] /= n;
+    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f [res_wait %.0f tmem %.0f math %.0f store %.0f]\n",
+            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
   }
   return 0;
 }
