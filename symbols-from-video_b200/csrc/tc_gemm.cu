@@ -266,11 +266,14 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
       ::"r"(bar), "h"(mask)
       : "memory");
 }
+// Remote arrive on the barrier at the same offset in CTA `cta`.  Default (.release.cta) semantics as in CUTLASS'
+// ClusterBarrier::arrive: a .cluster-scope release costs a full membar (+L1 invalidate, ~1600 cycles per tile measured);
+// the TMEM hand-over is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar_local), "r"(cta)
       : "memory");
 }
@@ -357,6 +360,22 @@ constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias 
 // three horizontal taps of a filter row; the MMAs read it at start addresses shifted by one pixel
 // (128 B) per tap.  Cuts the A operand's TMA->smem traffic 3x on the layers where the shared-memory
 // port, not the tensor pipe, bounds the main loop (Cout = 128).
+// Per-lane partial sums only (no cross-lane traffic): acc[2g], acc[2g+1] += sum / sum of squares of group g of this
+// lane's row.  Used by the 8-warp epilogue, which reduces across lanes once per image instead of once per chunk.
+template <int CPG>
+__device__ __forceinline__ void epi_stats_lane(const float* f, bool valid, float* acc) {
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float t = valid ? f[g * CPG + j] : 0.f;
+      s += t; q = fmaf(t, t, q);
+    }
+    acc[2 * g] += s; acc[2 * g + 1] += q;
+  }
+}
+
 template <int BLOCK_N, int NCTA, bool HALO = false>
 struct Cfg {
   static constexpr int kGroup = HALO ? 3 : 1;                           // filter taps per pipeline stage
@@ -600,6 +619,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       __syncwarp();
     };
+    // kSets == 2 (Cout = 128, 4 channels per group): per-lane register partials for this warp's 16 groups,
+    // reduced across the 32 rows once per image (one 32-value recursive-halving pass, 31 shuffles)
+    constexpr bool kRegStats = C::kSets == 2;
+    float gacc[kRegStats ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (kRegStats ? 32 : 1); ++i) gacc[i] = 0.f;
+    auto gn_flush_regs = [&]() {
+      if constexpr (kRegStats) {
+        int idx;
+        const float r = halving_reduce<32>(gacc, lane, idx);
+        const int grp = (gn_nt * BLOCK_N + cbase) / 4 + (idx >> 1);
+        if (grp < p.gn_groups)
+          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (idx & 1)], (double)r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) gacc[i] = 0.f;
+      }
+    };
     int bias_nt = -1;
     auto load_bias = [&](int n_tile) {      // per-warp shared copy: L1 is ~empty with this much smem carved out
       if (n_tile == bias_nt) return;
@@ -614,7 +650,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
     unsigned long long t_tfull = 0, t_start = clock64();
-    unsigned long long t_e[4] = {0, 0, 0, 0};   // debug: residual wait | tmem wait | math+stats+staging | store issue+wait
+    unsigned long long t_e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // debug: residual wait | tmem wait | math+stats+staging | store issue+wait | tile prologue | tile epilogue
     constexpr int kNChunk = kColsPerSet / C::kChunk;      // chunks of 32 columns this warp handles per tile
     const bool use_tma = C::kChunk == 32 && p.epi_mode == 1;
     const bool has_res = p.residual != nullptr;
@@ -646,6 +682,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int g = 0; g < kResBufs - 1; ++g) issue_residual(g);
     }
     for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+      const unsigned long long t_top = p.dbg ? clock64() : 0;
       const int n_tile = unit % p.n_tiles_n;
       const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
       const bool tile_ok = m_tile < p.n_tiles_m;
@@ -656,11 +693,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = tile_ok && (x < p.Wo) && (y < p.Ho);
       const long long row_off = (((long long)img * p.Ho + y) * p.Wo + x) * p.ldo;
       if (p.gn_stats && tile_ok && (img != gn_img || n_tile != gn_nt)) {
-        if (gn_img >= 0) gn_flush();
+        if (gn_img >= 0) { if (kRegStats && p.gn_cpg == 4) gn_flush_regs(); else gn_flush(); }
         gn_img = img; gn_nt = n_tile;
       }
       load_bias(n_tile);
       const unsigned long long tw = p.dbg ? clock64() : 0;
+      if (p.dbg) t_e[4] += tw - t_top;
       ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, abort_flag, p.err, 4);
       if (p.dbg) t_tfull += clock64() - tw;
       if (!ok) break;
@@ -673,7 +711,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           //      swizzled staging tiles, so shared-memory accesses are conflict-free.
           const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
           const int sw16 = (lane >> 1) & 3;        // 64B swizzle:  chunk j of row r lives at j ^ ((r >> 1) & 3)
-#pragma unroll 1
+#pragma unroll (kRegStats ? 2 : 1)
           for (int c = 0; c < kNChunk; ++c, ++g_cur) {
             const int c0 = c * 32;                              // column inside this warp's share
             const int col0 = n_tile * BLOCK_N + cbase + c0;
@@ -712,11 +750,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
               }
+              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[6] += t1 - tq; tq = t1; }
               if (p.gn_stats) {   // statistics of the finished fp32 values (bias and residual included)
-                if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
+                if (kRegStats && p.gn_cpg == 4) epi_stats_lane<4>(f, row_ok, gacc + (kRegStats ? c * 16 : 0));
+                else if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
                 else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
                 else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
               }
+              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[7] += t1 - tq; tq = t1; }
               if (p.out_f32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -733,6 +774,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   *reinterpret_cast<uint4*>(hb + ((j ^ sw16) << 4)) = u;
                 }
               }
+              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[8] += t1 - tq; tq = t1; }
               fence_proxy_async();
               __syncwarp();
               if (p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
@@ -786,7 +828,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (p.gn_stats) {
-              if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
+              if (kRegStats && p.gn_cpg == 4) {
+                if (c0 == 0) epi_stats_lane<4>(f, row_ok, gacc); else epi_stats_lane<4>(f, row_ok, gacc + (kRegStats ? 16 : 0));
+              }
+              else if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
               else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
               else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
             }
@@ -821,6 +866,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      const unsigned long long t_end0 = p.dbg ? clock64() : 0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -828,15 +874,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(smem_u32(&tempty_bar[acc]));
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.dbg) t_e[5] += clock64() - t_end0;
     }
     if (use_tma) {      // staging tiles must outlive the bulk stores that read them
       if (elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       __syncwarp();
     }
-    if (p.gn_stats && gn_img >= 0) gn_flush();
+    if (p.gn_stats && gn_img >= 0) { if (kRegStats && p.gn_cpg == 4) gn_flush_regs(); else gn_flush(); }
     if (p.dbg && warp == 2 && lane == 0) {
       p.dbg[blockIdx.x * 16 + 5] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 6] = t_tfull;
       p.dbg[blockIdx.x * 16 + 7] = t_e[0]; p.dbg[blockIdx.x * 16 + 8] = t_e[1]; p.dbg[blockIdx.x * 16 + 9] = t_e[2]; p.dbg[blockIdx.x * 16 + 10] = t_e[3];
+      p.dbg[blockIdx.x * 16 + 11] = t_e[4]; p.dbg[blockIdx.x * 16 + 12] = t_e[5];
+      p.dbg[blockIdx.x * 16 + 13] = t_e[6]; p.dbg[blockIdx.x * 16 + 14] = t_e[7]; p.dbg[blockIdx.x * 16 + 15] = t_e[8];
     }
   }
 
@@ -937,8 +986,8 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     double a[16] = {0}; int n = 0;
     for (int b = 0; b < grid; b += NCTA) { for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k]; ++n; }
     for (int k = 0; k < 16; ++k) a[k] /= n;
-    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f [res_wait %.0f tmem %.0f math %.0f store %.0f]\n",
-            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f [res_wait %.0f tmem %.0f fence %.0f store %.0f | tile_pre %.0f tile_post %.0f | fma %.0f stats %.0f pack_sts %.0f]\n",
+            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
   }
   return 0;
 }
