@@ -177,6 +177,117 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
   }
 }
 
+// ---- bulk-async fed variant -----------------------------------------------------
+// A block's slab of pixels is one contiguous byte range in NHWC, so the input is streamed
+// through a 4-slot shared-memory ring with cp.async.bulk (the TMA engine keeps 64 KB per block in
+// flight with no registers or issue slots spent on address generation); the 256 threads normalise
+// from shared memory and write 16-byte coalesced outputs.  grid (slabs, N), block 256, 64 KB smem.
+constexpr int kBulkSlots = 4;
+constexpr int kBulkPieceBytes = 16384;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool IN16, bool OUT16>
+__global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __restrict__ x, const double* __restrict__ stats,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, void* __restrict__ y,
+                                                               int fmt, long long HW, int C, int G, float eps,
+                                                               int do_silu, int pix_per_block) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ float sh_mean[64], sh_rstd[64];
+  __shared__ __align__(8) uint64_t full[kBulkSlots];
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  constexpr int ES = IN16 ? 2 : 4;
+  const int pix_bytes = C * ES;
+  const int ppp = kBulkPieceBytes / pix_bytes;            // pixels per piece
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(p0 + (long long)pix_per_block, HW);
+  const int npieces = (int)((p1 - p0 + ppp - 1) / ppp);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + ((long long)n * HW + p0) * pix_bytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBulkSlots; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < G) {
+    const double cnt = (double)HW * cpg;
+    const double m = stats[((long long)n * G + threadIdx.x) * 2] / cnt;
+    double var = stats[((long long)n * G + threadIdx.x) * 2 + 1] / cnt - m * m;
+    if (var < 0) var = 0;
+    sh_mean[threadIdx.x] = (float)m;
+    sh_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  auto issue = [&](int piece) {
+    const long long pp0 = (long long)piece * ppp;
+    const long long cntp = min((long long)ppp, (p1 - p0) - pp0);
+    const uint32_t bytes = (uint32_t)(cntp * pix_bytes);
+    const uint32_t bar = smem_addr(&full[piece % kBulkSlots]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(ring + (piece % kBulkSlots) * kBulkPieceBytes)), "l"(src + pp0 * pix_bytes), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBulkSlots && i < npieces; ++i) issue(i);
+  const int tpp = C >> 3;
+  const int rows = 256 / tpp;
+  const int tc = threadIdx.x % tpp;
+  const int tr = threadIdx.x / tpp;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = tc * 8 + j;
+    const int g = c / cpg;
+    sc[j] = gamma[c] * sh_rstd[g];
+    sf[j] = beta[c] - sh_mean[g] * sc[j];
+  }
+  for (int piece = 0; piece < npieces; ++piece) {
+    const int slot = piece % kBulkSlots;
+    const uint32_t bar = smem_addr(&full[slot]);
+    const uint32_t parity = (uint32_t)((piece / kBulkSlots) & 1);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    const long long pp0 = (long long)piece * ppp;
+    const int cntp = (int)min((long long)ppp, (p1 - p0) - pp0);
+    const uint8_t* buf = ring + slot * kBulkPieceBytes;
+    for (int r = tr; r < cntp; r += rows) {
+      float v[8];
+      if (IN16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(buf + (r * C + tc * 8) * 2);
+        unpack2_16(u.x, fmt, v[0], v[1]); unpack2_16(u.y, fmt, v[2], v[3]);
+        unpack2_16(u.z, fmt, v[4], v[5]); unpack2_16(u.w, fmt, v[6], v[7]);
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(buf + (r * C + tc * 8) * 4);
+        const float4 b = *reinterpret_cast<const float4*>(buf + (r * C + tc * 8) * 4 + 16);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(v[j], sc[j], sf[j]);
+        v[j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
+      }
+      const long long idx = ((long long)n * HW + p0 + pp0 + r) * C + tc * 8;
+      if (OUT16) {
+        uint4 o;
+        o.x = pack2_16(v[0], v[1], fmt); o.y = pack2_16(v[2], v[3], fmt);
+        o.z = pack2_16(v[4], v[5], fmt); o.w = pack2_16(v[6], v[7], fmt);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + idx) = o;
+      } else {
+        float* o = reinterpret_cast<float*>(y) + idx;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    __syncthreads();                       // everyone is done reading this slot
+    if (threadIdx.x == 0 && piece + kBulkSlots < npieces) issue(piece + kBulkSlots);
+  }
+}
+
 __global__ void gn_apply_scalar_kernel(const float* x, const double* stats, const float* gamma,
                                        const float* beta, float* y, long long HW, int C, int G,
                                        float eps, int do_silu, long long total) {
@@ -349,6 +460,26 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
     const int rows = 256 / (C / 8);
     ppb = (ppb + rows * 8 - 1) / (rows * 8) * (rows * 8);
     dim3 grid((unsigned)((HW + ppb - 1) / ppb), N);
+    static int bulk = -1;
+    if (bulk < 0) { const char* e = getenv("SFV_GN_BULK"); bulk = e ? atoi(e) : 1; }
+    const int pix_bytes = C * (x_is16 ? 2 : 4);
+    if (bulk && kBulkPieceBytes % pix_bytes == 0 && ((uintptr_t)x & 15) == 0) {
+      static bool attr = false;
+      if (!attr) {
+        SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
+        SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
+        SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
+        SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
+        attr = true;
+      }
+      const size_t sm = kBulkSlots * kBulkPieceBytes;
+      if (x_is16 && y_is16) gn_apply_bulk_kernel<true, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+      else if (!x_is16 && y_is16) gn_apply_bulk_kernel<false, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+      else if (x_is16 && !y_is16) gn_apply_bulk_kernel<true, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+      else gn_apply_bulk_kernel<false, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+      SFV_LAUNCH_OK();
+      return 0;
+    }
     if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
     else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
     else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
