@@ -50,6 +50,7 @@ struct TcParams {
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
   int epi_mode;
   int halo_base_offset;
+  int num_stages, res_bufs, h16_slots;   // shared-memory plan of this launch
   int a2_kchunks, a2_k0;               // fused 1x1 branch: extra k-chunks read through the second A map
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
@@ -387,16 +388,23 @@ struct Cfg {
   static constexpr int kSets = BLOCK_N == 128 ? 2 : 1;               // epilogue warps per TMEM lane quarter
   static constexpr int kEpiWarps = 4 * kSets;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kResBufs = kSets == 2 ? 2 : 3;                // fp32 staging ring slots per warp
-  static constexpr int kEpiF32Bytes = kEpiWarps * kResBufs * 4096;
-  static constexpr int kEpiH16Bytes = kEpiWarps * 2 * 2048;
-  static constexpr int kEpiBytes = BLOCK_N >= 32 ? (kEpiF32Bytes + kEpiH16Bytes) : 0;
-  static constexpr int kBudget = 232448 - 1024 - kAuxBytes - kEpiBytes;
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  // The staging rings are sized per launch (a conv that writes only 16-bit outputs needs no fp32 ring), and
+  // whatever shared memory is left becomes pipeline stages: res_bufs fp32 slots (0, 2 or 3) and h16_slots
+  // (0 or 2) per epilogue warp, see smem_plan().
+  static constexpr int kMaxStages = 8;
+  static constexpr int kSmemLimit = 232448;
+  static __host__ __device__ constexpr int epi_bytes(int res_bufs, int h16_slots) {
+    return BLOCK_N >= 32 ? kEpiWarps * (res_bufs * 4096 + h16_slots * 2048) : 0;
+  }
+  static __host__ constexpr int stages_for(int res_bufs, int h16_slots) {
+    const int n = (kSmemLimit - 1024 - kAuxBytes - epi_bytes(res_bufs, h16_slots)) / kStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kAuxBytes + 1024 /*align slack*/;
-  static_assert(kStages >= (HALO ? 2 : 3), "pipeline too shallow");   // a HALO stage carries 12 MMAs
+  static __host__ constexpr int smem_bytes(int stages, int res_bufs, int h16_slots) {
+    return stages * kStageBytes + epi_bytes(res_bufs, h16_slots) + kAuxBytes + 1024 /*align slack*/;
+  }
 };
 
 template <int BLOCK_N, int NCTA, bool HALO>
@@ -412,16 +420,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* epi_f32 = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are)
-  uint8_t* epi_h16 = epi_f32 + (C::kEpiBytes ? C::kEpiF32Bytes : 0);
-  constexpr int kResBufs = C::kResBufs;
-  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes + C::kEpiBytes);
+  const int num_stages = p.num_stages;
+  const int kResBufs = p.res_bufs;                                        // fp32 staging slots per epilogue warp (runtime)
+  uint8_t* epi_f32 = smem + num_stages * C::kStageBytes;                  // 1024-aligned (stage sizes are)
+  uint8_t* epi_h16 = epi_f32 + C::kEpiWarps * kResBufs * 4096;
+  uint64_t* bars = (uint64_t*)(smem + num_stages * C::kStageBytes + C::epi_bytes(kResBufs, p.h16_slots));
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::kStages;
-  uint64_t* tfull_bar = bars + 2 * C::kStages;
-  uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
-  uint64_t* res_bar = bars + 2 * C::kStages + 4;                           // [epilogue warps][kResBufs]
-  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * kResBufs);
+  uint64_t* empty_bar = bars + C::kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * C::kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * C::kMaxStages + 2;
+  uint64_t* res_bar = bars + 2 * C::kMaxStages + 4;                        // [epilogue warps][3]
+  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * 3);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
   float* gn_acc = (float*)((uint8_t*)bars + 512);        // [epilogue warps][512 / warps floats]: (sum, sumsq) per group
   float* bias_all = gn_acc + 512;                        // [epilogue warps][1024 / warps floats]
@@ -430,7 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < num_stages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
@@ -438,7 +447,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&tfull_bar[i]), 1);
       mbar_init(smem_u32(&tempty_bar[i]), C::kEpiWarps * NCTA);
     }
-    for (int i = 0; i < C::kEpiWarps * kResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    for (int i = 0; i < C::kEpiWarps * 3; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     *abort_flag = 0;
     fence_barrier_init();
   }
@@ -501,7 +510,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
         }
         {
@@ -526,7 +535,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -583,7 +592,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -657,7 +666,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
     uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
     uint8_t* h16_w = epi_h16 + ew * (2 * 2048);
-    uint64_t* res_bar_w = res_bar + ew * kResBufs;
+    uint64_t* res_bar_w = res_bar + ew * 3;
     auto issue_residual = [&](int g) {      // whole warp calls; one elected lane issues
       const int seq = g / kNChunk, c = g - seq * kNChunk;
       const int unit = unit0 + seq * unit_step;
@@ -718,7 +727,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool chunk_ok = tile_ok && col0 < p.Cout;     // warp-uniform
             uint32_t v[32];
             tmem_ld32(t_row + cbase + c0, v);
-            const int slot = g_cur % kResBufs;
+            const int slot = kResBufs ? g_cur % kResBufs : 0;
             uint8_t* fb = f32_w + slot * 4096 + lane * 128;
             float f[32];
             unsigned long long tq = p.dbg ? clock64() : 0;
@@ -957,21 +966,30 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
 
 template <int BLOCK_N, int NCTA, bool HALO = false>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mr, const CUtensorMap& mo32,
-               const CUtensorMap& mo16, const TcParams& p, cudaStream_t s, const char* tag) {
+               const CUtensorMap& mo16, const TcParams& p_in, cudaStream_t s, const char* tag) {
   using C = Cfg<BLOCK_N, NCTA, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
     SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
+                                  C::kSmemLimit));
     attr_set = true;
   }
+  // shared-memory plan: staging rings only where this launch needs them, the rest goes to pipeline stages
+  TcParams p = p_in;
+  const bool need_f32 = p.epi_mode == 1 && (p.residual || p.out_f32);
+  const bool need_h16 = p.epi_mode == 1 && p.out_16;
+  p.h16_slots = need_h16 ? 2 : 0;
+  p.res_bufs = !need_f32 ? 0 : ((C::kSets == 2 && need_h16) ? 2 : 3);
+  p.num_stages = C::stages_for(p.res_bufs, p.h16_slots);
+  SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
+  const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots);
   const int max_units = g_num_sms / NCTA;
   const int grid = (p.n_units < max_units ? p.n_units : max_units) * NCTA;
   // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
   const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
   ProfScope prof(PROF_TC_GEMM, flops, s, tag);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
