@@ -16,7 +16,7 @@ import os
 import numpy as np
 import torch
 
-from . import frames, kl_f8, rbvae, ref_shim
+from . import chinchess, frames, kl_f8, rbvae, ref_shim
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -91,9 +91,58 @@ def resize_case():
     print("resize_pil checksum", int(u8.astype(np.int64).sum()))
 
 
+def chinchess_case():
+    """The reference's sample video (480 frames; videos/frames/transition_flags.txt: chinese_chess) through
+    the UNMODIFIED reference classes: load_img's LANCZOS resize + crop (get_percep_embeddings.py:48-71, at a
+    128x72 target so the fixture stays small), AutoencoderKL.encode -> 0.18215*mode()
+    (embedding_matching.py:131-136), percep Seq2SeqBinaryVAE.encode(hard=True, noise_ratio=0).
+    Frames are stored as wrap-around deltas between consecutive frames (deflate-friendly)."""
+    import cv2
+    from PIL import Image
+    H, W = chinchess.HW
+    cap = cv2.VideoCapture(os.path.join(ref_shim.REF_ROOT, "videos/chinchess_gettyimages-148739276-640_adpp.mp4"))
+    fr = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        img = Image.fromarray(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)).convert("RGB")
+        img = img.resize((W, 72), resample=Image.LANCZOS).crop((0, 0, W, H))
+        fr.append(np.array(img))
+    u8 = np.stack(fr)
+    assert u8.shape == (480, H, W, 3), u8.shape
+    L = chinchess.L
+    sd = kl_f8.init_state_dict(0)
+    m = ref_shim.autoencoder_kl(sd)
+    rsd, (fh, fw) = chinchess.rbvae_weights()
+    rb = ref_shim.rbvae("percep", 4, L, rsd, feat_hw=(fh, fw))
+    lat, hs, zs = [], [], []
+    with torch.no_grad():
+        for i in range(0, 480, 32):
+            x = frames.normalise_u8(u8[i:i + 32])
+            z = 0.18215 * m.encode(x).mode()
+            lat.append(z)
+            xi = z.unsqueeze(1)
+            zs.append(rb.encode(xi, temperature=0.5, hard=True, noise_ratio=0.0)[:, 0])
+            logits = rb.encoder_cnn(z).reshape(-1, 1, L)
+            hs.append(rb.encoder_rnn(logits)[0][:, 0])
+    lat = torch.cat(lat).numpy(); hs = torch.cat(hs).numpy(); zs = torch.cat(zs).numpy()
+    delta = u8.copy()
+    delta[1:] = u8[1:] - u8[:-1]                       # uint8 wrap-around
+    np.savez_compressed(os.path.join(OUT, "chinchess_480x64x128.npz"), frame_delta=delta, weight_seed=0,
+                        L=L, latent_sum=lat.astype(np.float64).sum(axis=(1, 2, 3)),
+                        latent_first=lat[:2], latent_last=lat[-1:], h=hs, z_hard=zs,
+                        transitions=np.array([74, 206, 282, 389]), grey_out=10)
+    print("chinchess: min|h|", float(np.abs(hs).min()), "in-band", int((np.abs(hs) < 1e-3).sum()),
+          "distinct codes", len(np.unique(zs, axis=0)))
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-chinchess" in sys.argv:
+        return chinchess_case()
     encoder_case("kl_f8_seed0_2x64x96_white", 0, (2, 64, 96), 1234, False)
     encoder_case("kl_f8_seed1_1x128x128_smooth", 1, (1, 128, 128), 1234, True)
     encoder_case("kl_f8_seed0_2x256x256_white", 0, (2, 256, 256), 1234, False)      # BASELINE config 1 shape
@@ -103,6 +152,7 @@ def main():
     rbvae_case("rbvae_percep_L50_32x32_T4", "percep", 4, 256, 4, 50, (32, 32), 4, 4)
     rbvae_case("rbvae_contrastive_L25_256x256_T1", "contrastive", 3, 64, 2, 25, (256, 256), 5, 1)
     resize_case()
+    chinchess_case()
 
 
 if __name__ == "__main__":

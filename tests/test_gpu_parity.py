@@ -105,5 +105,10 @@ def test_contrastive_rbvae_512(prec):
     print(_c().check_contrastive_512(prec))
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_chinchess_480_frame_code_match(prec):
+    print(_c().check_chinchess_video(prec))
+
+
 def test_edge_cases_and_errors():
     print(_c().check_edge_cases())

@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from oracle import frames, kl_f8, primitives_np, rbvae, ref_shim
+from oracle import chinchess, frames, kl_f8, primitives_np, rbvae, ref_shim
 
 from conftest import GOLDEN
 
@@ -190,3 +190,26 @@ def test_oracle_matches_live_reference_rbvae():
     z, h = rbvae.encode(x, sd, temperature=1.0, hard=True, noise_ratio=0.0, return_h=True)
     assert (h - h_ref).abs().max() < 2e-7
     assert torch.equal(z, z_ref)
+
+
+def test_chinchess_oracle_matches_reference_golden():
+    """Sample-video fixture (reference classes on the 480 chinchess frames): the oracle on a slice of it."""
+    g = np.load(os.path.join(GOLDEN, "chinchess_480x64x128.npz"))
+    u8 = chinchess.frames_from_delta(g["frame_delta"])
+    assert u8.shape == (480,) + chinchess.HW + (3,)
+    sd = kl_f8.init_state_dict(int(g["weight_seed"]))
+    rsd, _ = chinchess.rbvae_weights()
+    idx = np.array([0, 1, 75, 207, 283, 390, 479])          # first two, one after each transition, last
+    post = kl_f8.encode(frames.normalise_u8(u8[idx]), sd)
+    lat = kl_f8.first_stage_encoding(post, use_mode=True)
+    assert rel_l2(lat[:2], g["latent_first"]) < 2e-6
+    assert rel_l2(lat[-1:], g["latent_last"]) < 2e-6
+    np.testing.assert_allclose(lat.double().sum(dim=(1, 2, 3)).numpy(), g["latent_sum"][idx], atol=2e-4)
+    z, h = rbvae.encode(lat[:, None], rsd, hard=True, noise_ratio=0.0, return_h=True)
+    h = h[:, 0].numpy(); z = z[:, 0].numpy()
+    np.testing.assert_allclose(h, g["h"][idx], atol=2e-6)
+    band = np.abs(g["h"][idx]) < 1e-5
+    assert ((z != g["z_hard"][idx]) & ~band).sum() == 0
+    # the fixture itself: codes follow the frames, and some |h| sit inside the exemption band
+    assert len(np.unique(g["z_hard"], axis=0)) > 8
+    assert 0 < (np.abs(g["h"]) < 1e-3).sum() < g["h"].size // 4

@@ -48,6 +48,8 @@ def plan():
     items += [("native/fp16", "check_native_frame_size('fp16')"), ("native/bf16", "check_native_frame_size('bf16')"),
               ("large1024/bf16", "check_large_frame_properties('bf16',1024,2)"),
               ("contrastive512/fp32", "check_contrastive_512('fp32')"), ("contrastive512/bf16", "check_contrastive_512('bf16')"),
+              ("chinchess/fp32", "check_chinchess_video('fp32')"), ("chinchess/fp16", "check_chinchess_video('fp16')"),
+              ("chinchess/bf16", "check_chinchess_video('bf16')"),
               ("edge", "check_edge_cases()")]
     return items
 
