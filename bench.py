@@ -91,6 +91,12 @@ def build_models(precision):
     return vae, rb, sd, rsd
 
 
+def workload_name(batch):
+    """The one workload both arms are quoted on (BASELINE.json configs[1])."""
+    return (f"BASELINE configs[1]: percep pipeline {R}x{R} uint8 frames -> KL-f8 encoder -> "
+            f"4x{R // 8}x{R // 8} latent -> RBVAE binary code (latent_dim {LATENT_DIM}), batch {batch} per GPU")
+
+
 def cpu_port_fps(sd, rsd, n_frames, frames_u8):
     """Oracle port of the reference CPU path (fp32, all host threads) on n_frames frames."""
     import torch
@@ -129,8 +135,10 @@ def run_reference(args, rank, world):
     line = dict(impl="reference", metric="frames_per_sec_512x512_to_binary_code", value=val, unit="frames/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * tot / len(times),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"percep pipeline {R}x{R} -> code, latent_dim {LATENT_DIM}",
-                            frames_per_step=sample),
+                config=dict(workload=workload_name(args.batch), frames_per_step_per_gpu=args.batch,
+                            weights="seeded random init (no checkpoint offline)",
+                            sample_frames_per_step=sample, operand_format="f32",
+                            note="CPU arm: each step is a bounded sample of the batch (same frames, same weights)"),
                 cpu_baseline=dict(value=val, unit="frames/s", cores=os.cpu_count(), kind="port",
                                   sample=f"{sample} frames of {R}x{R} per step, fp32, torch CPU"),
                 e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -146,6 +154,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SFV_PRECISION", "bf16"))
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-precision", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -282,13 +291,36 @@ def main():
                       flips_inside_band=int((diff & band).sum()), sample_frames=n_cpu,
                       h_maxabs=float(np.abs(r.h.cpu().numpy() - ref["h"]).max()))
 
+    # ---- the other 16-bit operand format on the same workload (device-resident, same timing rules) ----
+    alt = None
+    if world == 1 and not args.no_alt_precision and args.precision in ("bf16", "fp16"):
+        ap_ = "fp16" if args.precision == "bf16" else "bf16"
+        del pipe, vae, rb
+        torch.cuda.empty_cache()
+        vae2, rb2, _, _ = build_models(ap_)
+        pipe2 = sfv_b200.FramePipeline(vae2, rb2, batch=B, device=dev)
+        for i in range(3):
+            pipe2.encode_device(devbuf[i % N_INPUT_BUFFERS])
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for i in range(args.steps):
+            pipe2.encode_device(devbuf[i % N_INPUT_BUFFERS])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        alt = dict(operand_format=ap_, value=B * args.steps / (e0.elapsed_time(e1) / 1e3), unit="frames/s")
+        if parity is not None:
+            r2 = pipe2.encode_device(devbuf[0][:parity["sample_frames"]].contiguous())
+            z2 = sfv_b200.unpack_codes(r2.codes.cpu(), LATENT_DIM).numpy()
+            d2 = z2 != ref["z"]
+            alt.update(latent_rel_l2=float((r2.latents.cpu() - ref["lat"]).norm() / ref["lat"].norm()),
+                       flips_outside_band=int((d2 & ~band).sum()), flips_inside_band=int((d2 & band).sum()))
+        vae2.check_async_error()
+
     line = dict(
         metric="frames_per_sec_512x512_to_binary_code", value=value, unit="frames/s", n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype=args.precision, data="synthetic",
-        config=dict(workload=f"BASELINE configs[1]: percep pipeline {R}x{R} uint8 frames -> KL-f8 encoder -> "
-                             f"4x{R // 8}x{R // 8} latent -> RBVAE binary code (latent_dim {LATENT_DIM}), batch {B} per GPU",
-                    frames_per_step_per_gpu=B, weights="seeded random init (no checkpoint offline)",
+        config=dict(workload=workload_name(B), frames_per_step_per_gpu=B, weights="seeded random init (no checkpoint offline)",
                     l2_policy=f"{N_INPUT_BUFFERS} rotating input batches (> L2) and a multi-GB activation working set",
                     operand_format=args.precision, parallelism=f"frames sharded x{world}, all_gather(codes, latents)"),
         e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -308,7 +340,7 @@ def main():
                                 if v["ms"] > 0 else None,
                                 rate_unit="TFLOP/s" if k in ("tc_gemm", "igemm_f32") else "GB/s")
                         for k, v in prof.items()},
-        cpu_baseline=cpu, parity=parity)
+        cpu_baseline=cpu, parity=parity, alt_precision=alt)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

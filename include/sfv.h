@@ -171,6 +171,26 @@ int sfv_rbvae_encode(SfvRbvae* rb, const float* x, int32_t B, int32_t T, float i
 int sfv_hamming(const uint32_t* a, int32_t Na, const uint32_t* b, int32_t Nb, int32_t words,
                 int32_t* out, void* stream);
 
+/* State consistency on packed codes
+ * (scripts/evaluation/state_consistency_eval/embedding_matching.py:275-297; the same
+ * block in models/percep_RBVAE/percep_RBVAE_train.py:473-497): for every state s,
+ * best_count[s] = number of frames labelled s whose code equals the state's most common
+ * code, state_count[s] = frames labelled s.  percentage_s = best/state, weighted average =
+ * sum(best)/sum(state).  codes uint32 [n,words], labels int32 [n] in [0,n_states)
+ * (labels outside the range are ignored), words <= 8. */
+int sfv_state_consistency(const uint32_t* codes, const int32_t* labels, int64_t n, int32_t words,
+                          int32_t n_states, int32_t* best_count, int32_t* state_count, void* stream);
+
+/* Robustness perturbations on uint8 HWC frames (embedding_matching.py:141-193 followed by
+ * T.ToPILImage() at :243): out = byte(255 * clamp(u8/255 + (noise*std + mean), 0, 1)) when
+ * noise != NULL (noise fp32 [B,3,H,W], the CHW layout randn_like(ToTensor(img)) draws in);
+ * then, when occ_size > 0 and occ_xy != NULL (device int32 [B,2] = (x,y) per frame, the
+ * reference draws a fresh position per frame), the square [y,y+occ_size) x [x,x+occ_size) is
+ * set to 127 (= byte(0.5*255)).  in == out is allowed. */
+int sfv_perturb_frames(const uint8_t* frames, uint8_t* out, int32_t B, int32_t H, int32_t W,
+                       const float* noise_or_null, float mean, float std,
+                       const int32_t* occ_xy_or_null, int32_t occ_size, void* stream);
+
 /* ---- single-operator entry points (parity bisection of the kernels) --------
  * All tensors NHWC; `precision` picks the CUDA-core fp32 kernel or the tcgen05
  * kernel with bf16/fp16 operands (x and w are given in fp32 and converted by a

@@ -137,12 +137,64 @@ def chinchess_case():
           "distinct codes", len(np.unique(zs, axis=0)))
 
 
+def evaluation_case():
+    """The reference's own add_gaussian_noise / add_occlusion / calculate_state_consistency
+    (embedding_matching.py:141-297, executed unmodified through ref_shim.embedding_matching_functions)
+    on small seeded inputs."""
+    import random
+    import torchvision.transforms as T
+    from PIL import Image
+    rng = np.random.default_rng(21)
+    imgs = rng.integers(0, 256, (3, 24, 40, 3), dtype=np.uint8)
+    flags = [50, 120, 200]
+    ns = ref_shim.embedding_matching_functions(flags=flags)
+    torch.manual_seed(5)
+    gauss = np.stack([np.array(T.ToPILImage()(ns["add_gaussian_noise"](T.ToTensor()(Image.fromarray(im)), mean=0.05, std=0.2)))
+                      for im in imgs])
+    torch.manual_seed(5)
+    noise = torch.cat([torch.randn(1, 3, 24, 40) for _ in imgs]).numpy()
+    random.seed(7)
+    occ = np.stack([np.array(T.ToPILImage()(ns["add_occlusion"](T.ToTensor()(Image.fromarray(im)), coverage=0.3)))
+                    for im in imgs])
+    random.seed(7)
+    size = int(np.sqrt(0.3 * 24 * 40))
+    xy = np.array([(random.randint(0, 40 - size), random.randint(0, 24 - size)) for _ in imgs], dtype=np.int32)
+    # state consistency: 300 frames, 70-bit codes drawn from a few prototypes per state with bit noise
+    L = 70
+    protos = rng.integers(0, 2, (8, L)).astype(np.float32)
+    which = rng.integers(0, 8, 300)
+    z = protos[which].copy()
+    flip = rng.random((300, L)) < 0.004
+    z[flip] = 1 - z[flip]
+
+    class DS:
+        frames = [torch.full((1, 1, 1), float(i)) for i in range(300)]
+        test_indices_per_state = [list(range(3, 50, 2)), list(range(50, 120)), [], list(range(201, 300, 3))]
+
+    class Model:
+        def eval(self):
+            pass
+
+        def encode(self, x, temperature, hard, noise_ratio):
+            return torch.from_numpy(z[int(x.flatten()[0])])[None, None]
+
+    weighted, pct = ns["calculate_state_consistency"](Model(), DS(), "cpu")
+    idx = np.array([i for st in DS.test_indices_per_state for i in st])
+    labels = np.array([ns["assign_label"](int(i), flags) for i in idx])
+    np.savez_compressed(os.path.join(OUT, "evaluation.npz"), imgs=imgs, gauss=gauss, noise=noise, gauss_mean=0.05,
+                        gauss_std=0.2, occ=occ, occ_xy=xy, occ_size=size, z=z, idx=idx, labels=labels,
+                        flags=np.array(flags), weighted=float(weighted), percentages=np.array(pct, dtype=np.float64))
+    print("evaluation: weighted", weighted, "pct", pct, "occ size", size, xy.tolist())
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     if "--only-chinchess" in sys.argv:
         return chinchess_case()
+    if "--only-evaluation" in sys.argv:
+        return evaluation_case()
     encoder_case("kl_f8_seed0_2x64x96_white", 0, (2, 64, 96), 1234, False)
     encoder_case("kl_f8_seed1_1x128x128_smooth", 1, (1, 128, 128), 1234, True)
     encoder_case("kl_f8_seed0_2x256x256_white", 0, (2, 256, 256), 1234, False)      # BASELINE config 1 shape
@@ -153,6 +205,7 @@ def main():
     rbvae_case("rbvae_contrastive_L25_256x256_T1", "contrastive", 3, 64, 2, 25, (256, 256), 5, 1)
     resize_case()
     chinchess_case()
+    evaluation_case()
 
 
 if __name__ == "__main__":

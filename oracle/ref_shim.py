@@ -90,3 +90,24 @@ def rbvae(kind, in_channels, latent_dim, sd=None, feat_hw=None):
         own.update({k: v for k, v in sd.items()})
         m.load_state_dict(own)
     return m.eval()
+
+
+def embedding_matching_functions(flags=()):
+    """The reference's evaluation helpers, UNMODIFIED, executed from their own source text:
+    scripts/evaluation/state_consistency_eval/embedding_matching.py imports omegaconf / ldm at module level
+    (absent here), so the four function definitions are cut out of the file with ``ast`` and exec'd in a
+    namespace holding exactly the globals they use (torch, np, random, torchvision.transforms as T, and the
+    module-level ``flags`` that __main__ sets, :389)."""
+    import ast
+    import random
+    import numpy as np
+    import torch
+    import torchvision.transforms as T
+    path = os.path.join(REF_ROOT, "scripts/evaluation/state_consistency_eval/embedding_matching.py")
+    src = open(path).read()
+    want = {"add_gaussian_noise", "add_occlusion", "assign_label", "calculate_state_consistency"}
+    ns = {"torch": torch, "np": np, "random": random, "T": T, "flags": list(flags)}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns

@@ -71,6 +71,9 @@ SIGNATURES = {
     "sfv_rbvae_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, _P, C.c_float, C.c_float, C.c_int32,
                                    _P, _P, _P, _P, C.c_size_t, _P]),
     "sfv_hamming": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P]),
+    "sfv_state_consistency": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
+    "sfv_perturb_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float,
+                                     _P, C.c_int32, _P]),
     "sfv_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int32] * 11 + [_P]),
     "sfv_op_group_norm": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_int32, _P]),

@@ -223,6 +223,21 @@ int sfv_hamming(const uint32_t* a, int32_t Na, const uint32_t* b, int32_t Nb, in
   return launch_hamming(a, Na, b, Nb, words, out, (cudaStream_t)stream);
 }
 
+int sfv_state_consistency(const uint32_t* codes, const int32_t* labels, int64_t n, int32_t words, int32_t n_states,
+                          int32_t* best_count, int32_t* state_count, void* stream) {
+  SFV_TRY(require_device());
+  if ((n > 0 && (!codes || !labels)) || !best_count || !state_count)
+    return fail(SFV_ERR_INVALID, "state_consistency: null argument");
+  return launch_state_consistency(codes, labels, n, words, n_states, best_count, state_count, (cudaStream_t)stream);
+}
+
+int sfv_perturb_frames(const uint8_t* frames, uint8_t* out, int32_t B, int32_t H, int32_t W, const float* noise_or_null,
+                       float mean, float std, const int32_t* occ_xy_or_null, int32_t occ_size, void* stream) {
+  SFV_TRY(require_device());
+  if (B > 0 && (!frames || !out)) return fail(SFV_ERR_INVALID, "perturb_frames: null argument");
+  return launch_perturb(frames, out, B, H, W, noise_or_null, mean, std, occ_xy_or_null, occ_size, (cudaStream_t)stream);
+}
+
 // ---- single-operator entry points (test-only: allocate scratch internally, synchronous) ----
 struct Scratch {
   std::vector<void*> p;

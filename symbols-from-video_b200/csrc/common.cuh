@@ -63,6 +63,7 @@ struct ProfScope {
 };
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // 16-bit operand formats of the tensor-core path.
@@ -165,6 +166,10 @@ int launch_fc(const float* x, const float* w, const float* bias, float* y, int N
               int L, float* partial, int splits, cudaStream_t s);
 int launch_hamming(const uint32_t* a, int Na, const uint32_t* b, int Nb, int words, int* out,
                    cudaStream_t s);
+int launch_state_consistency(const uint32_t* codes, const int* labels, long long n, int words, int n_states,
+                             int* best, int* count, cudaStream_t s);
+int launch_perturb(const uint8_t* in, uint8_t* out, int B, int H, int W, const float* noise, float mean,
+                   float stdv, const int* occ_xy, int osz, cudaStream_t s);
 
 // ---- tcgen05 conv / GEMM -----------------------------------------------------
 struct TcTap { int o[5]; };

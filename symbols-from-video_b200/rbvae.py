@@ -137,9 +137,12 @@ class Seq2SeqBinaryVAE(nn.Module):
         h = self._native(H, W)
         x = x.to(torch.float32).contiguous()
         dev = x.device
-        if U is None and noise_ratio != 0:
-            # same global-RNG CPU draw as binary_concrete_logits (percep_RBVAE_model.py:33)
+        if U is None:
+            # same global-RNG CPU draw as binary_concrete_logits (percep_RBVAE_model.py:33); the reference
+            # draws it even when noise_ratio == 0, so the generator state after the call matches too
             U = torch.rand(B * T, L)
+            if noise_ratio == 0:
+                U = None
         if U is not None:
             U = U.to(device=dev, dtype=torch.float32).reshape(B * T, L).contiguous()
         h_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)

@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 import sfv_b200  # noqa: E402
-from oracle import chinchess, frames, kl_f8, numerics_model, rbvae as orb  # noqa: E402
+from oracle import chinchess, evaluation as oev, frames, kl_f8, numerics_model, rbvae as orb  # noqa: E402
 
 DEV = "cuda"
 
@@ -443,6 +443,100 @@ def check_chinchess_video(prec="fp32"):
         assert o == 0 and out["h_maxabs"] < 1e-5, out
     else:
         assert o <= (0.002 if prec == "fp16" else 0.02) * z.size, out      # reported, see DESIGN 2
+    return out
+
+
+def check_evaluation_kernels():
+    """State consistency on packed codes and the uint8 perturbations: bit-exact against the
+    golden outputs of the reference's own functions and against the oracle on larger seeded cases."""
+    g = np.load(os.path.join(GOLDEN, "evaluation.npz"))
+    imgs = torch.from_numpy(g["imgs"]).to(DEV)
+    got = sfv_b200.perturb_frames(imgs, noise=torch.from_numpy(g["noise"]), mean=float(g["gauss_mean"]), std=float(g["gauss_std"]))
+    assert np.array_equal(got.cpu().numpy(), g["gauss"])
+    got = sfv_b200.perturb_frames(imgs, occ_xy=torch.from_numpy(g["occ_xy"]), occ_size=int(g["occ_size"]))
+    assert np.array_equal(got.cpu().numpy(), g["occ"])
+    z = torch.from_numpy(g["z"][g["idx"]])
+    codes = torch.from_numpy(orb.pack_codes(z).view(np.int32)).to(DEV)
+    w, pct, cnt = sfv_b200.state_consistency(codes, torch.from_numpy(g["labels"]), len(g["flags"]) + 1)
+    assert abs(w - float(g["weighted"])) < 1e-12 and np.allclose(pct, g["percentages"], atol=1e-12), (w, pct)
+    out = dict(golden_weighted=w, golden_pct=pct)
+    # larger seeded cases against the oracle: 1..4 words, heavy duplication, a state with no frames
+    rng = np.random.default_rng(0)
+    for L, N, S in ((25, 1000, 5), (64, 4099, 9), (100, 777, 3), (1, 300, 2)):
+        protos = rng.integers(0, 2, (6, L)).astype(np.float32)
+        zz = protos[rng.integers(0, 6, N)]
+        fl = rng.random((N, L)) < 0.01
+        zz[fl] = 1 - zz[fl]
+        labels = rng.integers(0, S, N)
+        labels[labels == 1] = 0                                   # state 1 stays empty
+        w_ref, p_ref = oev.state_consistency(zz, labels, S)
+        cw = torch.from_numpy(orb.pack_codes(torch.from_numpy(zz)).view(np.int32)).to(DEV)
+        w, pct, cnt = sfv_b200.state_consistency(cw, torch.from_numpy(labels), S)
+        assert abs(w - w_ref) < 1e-12 and np.allclose(pct, p_ref, atol=1e-12), (L, N, w, w_ref)
+        assert cnt == [int((labels == s).sum()) for s in range(S)]
+    # perturbations at video size, both at once, in place
+    u8 = frames.synthetic_frames(3, 432, 768, 9, smooth=True)
+    gen = torch.Generator().manual_seed(4)
+    nz = torch.randn(3, 3, 432, 768, generator=gen)
+    xy = np.array([(0, 0), (768 - 262, 432 - 262), (100, 50)], dtype=np.int32)
+    ref = np.stack([oev.occlusion_u8(oev.gaussian_noise_u8(u8[i], nz[i], 0.0, 0.1), int(xy[i, 0]), int(xy[i, 1]), 262)
+                    for i in range(3)])
+    buf = torch.from_numpy(u8).to(DEV)
+    sfv_b200.perturb_frames(buf, noise=nz, std=0.1, occ_xy=torch.from_numpy(xy), occ_size=262, out=buf)
+    assert np.array_equal(buf.cpu().numpy(), ref)
+    out["perturb_bit_exact"] = True
+    # empty inputs
+    w, pct, cnt = sfv_b200.state_consistency(torch.empty(0, 1, dtype=torch.int32, device=DEV), torch.empty(0, dtype=torch.int32), 3)
+    assert w == 0 and pct == [0.0, 0.0, 0.0]
+    return out
+
+
+def check_state_consistency_pipeline(prec="fp32"):
+    """calculate_state_consistency mirror (embedding_matching.py:208-297) on the chinchess fixture, every
+    6th frame, with posterior sampling and binary-concrete noise drawn from the seeded global RNG in the
+    reference's per-frame order, gaussian perturbation included; against the oracle run frame by frame."""
+    import random
+    g = np.load(os.path.join(GOLDEN, "chinchess_480x64x128.npz"))
+    u8 = chinchess.frames_from_delta(g["frame_delta"])
+    vae, sd = make_vae(prec, 0)
+    rsd, _ = chinchess.rbvae_weights()
+    H, W = chinchess.HW
+    L = chinchess.L
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, L, L, input_hw=(H // 8, W // 8), precision=prec)
+    rb.load_state_dict(rsd)
+    flags = [int(v) for v in g["transitions"]]
+    idx = list(range(0, 480, 6))
+    out = {}
+    for kind, params in ((None, None), ("gaussian", dict(std=0.05)), ("occlusion", dict(coverage=0.1))):
+        torch.manual_seed(123); random.seed(5)
+        w, pct, codes, labels = sfv_b200.calculate_state_consistency(
+            rb, u8, flags, idx, sd_model=sfv_b200.FirstStage(vae), temperature=0.5, noise_ratio=0.1,
+            perturbation=kind, perturbation_params=params, target_size=(W, H), batch=32, return_codes=True)
+        vae.check_async_error()
+        # oracle, one frame at a time, same draws in the same order
+        torch.manual_seed(123); random.seed(5)
+        zs, hs = [], []
+        occ = int(np.sqrt(0.1 * H * W))
+        for i in idx:
+            fr = u8[i]
+            if kind == "gaussian":
+                fr = oev.gaussian_noise_u8(fr, torch.randn(1, 3, H, W), 0.0, 0.05)
+            elif kind == "occlusion":
+                x = random.randint(0, W - occ); y = random.randint(0, H - occ)
+                fr = oev.occlusion_u8(fr, x, y, occ)
+            post = kl_f8.encode(frames.normalise_u8(fr[None]), sd)
+            lat = kl_f8.first_stage_encoding(post, noise=torch.randn(1, 4, H // 8, W // 8))
+            U = torch.rand(1, L)
+            z, h = orb.encode(lat[:, None], rsd, temperature=0.5, hard=True, noise_ratio=0.1, U=U, return_h=True)
+            zs.append(z[0, 0].numpy()); hs.append((h[0, 0] + orb.logistic_noise(U, 0.1)[0]).numpy())
+        zs = np.stack(zs); hs = np.stack(hs)
+        w_ref, p_ref = oev.state_consistency(zs, labels.numpy(), len(flags) + 1)
+        o, i_, n = code_flips(sfv_b200.unpack_codes(codes, L).cpu().numpy(), zs, hs)
+        out[str(kind)] = dict(weighted=w, weighted_ref=w_ref, flips_outside=o, flips_inside=i_, band=n)
+        if prec == "fp32":
+            assert o == 0, out
+            if i_ == 0:
+                assert abs(w - w_ref) < 1e-12 and np.allclose(pct, p_ref), out
     return out
 
 

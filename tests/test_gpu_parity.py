@@ -110,5 +110,14 @@ def test_chinchess_480_frame_code_match(prec):
     print(_c().check_chinchess_video(prec))
 
 
+def test_evaluation_kernels_bit_exact():
+    print(_c().check_evaluation_kernels())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_state_consistency_pipeline(prec):
+    print(_c().check_state_consistency_pipeline(prec))
+
+
 def test_edge_cases_and_errors():
     print(_c().check_edge_cases())

@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from oracle import chinchess, frames, kl_f8, primitives_np, rbvae, ref_shim
+from oracle import chinchess, evaluation as oev, frames, kl_f8, primitives_np, rbvae, ref_shim
 
 from conftest import GOLDEN
 
@@ -213,3 +213,38 @@ def test_chinchess_oracle_matches_reference_golden():
     # the fixture itself: codes follow the frames, and some |h| sit inside the exemption band
     assert len(np.unique(g["z_hard"], axis=0)) > 8
     assert 0 < (np.abs(g["h"]) < 1e-3).sum() < g["h"].size // 4
+
+
+def test_evaluation_oracle_matches_reference_golden():
+    """State consistency + perturbations: oracle restatement vs the outputs of the reference's own
+    functions (tests/golden/evaluation.npz, embedding_matching.py:141-297)."""
+    g = np.load(os.path.join(GOLDEN, "evaluation.npz"))
+    for i in range(g["imgs"].shape[0]):
+        got = oev.gaussian_noise_u8(g["imgs"][i], torch.from_numpy(g["noise"][i]), float(g["gauss_mean"]), float(g["gauss_std"]))
+        assert np.array_equal(got, g["gauss"][i])
+        x, y = (int(v) for v in g["occ_xy"][i])
+        assert np.array_equal(oev.occlusion_u8(g["imgs"][i], x, y, int(g["occ_size"])), g["occ"][i])
+    w, pct = oev.state_consistency(g["z"][g["idx"]], g["labels"], len(g["flags"]) + 1)
+    assert w == pytest.approx(float(g["weighted"]), abs=1e-12)
+    np.testing.assert_allclose(pct, g["percentages"], atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_evaluation_oracle_matches_live_reference():
+    import random
+    import torchvision.transforms as T
+    from PIL import Image
+    ns = ref_shim.embedding_matching_functions(flags=[4, 9])
+    rng = np.random.default_rng(3)
+    im = rng.integers(0, 256, (16, 24, 3), dtype=np.uint8)
+    torch.manual_seed(11)
+    ref = np.array(T.ToPILImage()(ns["add_gaussian_noise"](T.ToTensor()(Image.fromarray(im)), std=0.3)))
+    torch.manual_seed(11)
+    assert np.array_equal(oev.gaussian_noise_u8(im, torch.randn(1, 3, 16, 24), 0.0, 0.3), ref)
+    random.seed(2)
+    ref = np.array(T.ToPILImage()(ns["add_occlusion"](T.ToTensor()(Image.fromarray(im)), coverage=0.25)))
+    random.seed(2)
+    s = int(np.sqrt(0.25 * 16 * 24))
+    x = random.randint(0, 24 - s); y = random.randint(0, 16 - s)
+    assert np.array_equal(oev.occlusion_u8(im, x, y, s), ref)
+    assert [ns["assign_label"](i, [4, 9]) for i in (0, 3, 4, 8, 9, 100)] == [0, 0, 1, 1, 2, 2]
