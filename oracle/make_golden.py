@@ -187,6 +187,32 @@ def evaluation_case():
     print("evaluation: weighted", weighted, "pct", pct, "occ size", size, xy.tolist())
 
 
+DATASET_SEGMENTS = [(0, 37), (37, 90), (90, 101), (101, 160)]
+
+
+def dataset_embeddings(n=160, hw=(2, 3), seed=9):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(n, 4, *hw, generator=g).numpy()
+    # mixed key styles, as _load_embedding accepts both (:343-349)
+    return {(f"{i:010d}.jpg" if i % 3 else f"{i:010d}"): lat[i:i + 1] for i in range(n)}
+
+
+def dataset_case():
+    """Reference ShuffledStatePairDataset (percep_RBVAE_train.py:181-360) on a seeded toy embedding dict."""
+    import random
+    cls = ref_shim.train_dataset_class()
+    emb = dataset_embeddings()
+    out = {}
+    for mode in ("train", "val", "test"):
+        random.seed(31)
+        ds = cls(emb, DATASET_SEGMENTS, test_pct=0.15, val_pct=0.1, mode=mode)
+        out[mode + "_pairs"] = np.array([[list(p[i % len(p)]) for p in ds.pairs_per_state] for i in range(len(ds))])
+        out[mode + "_items"] = torch.stack([ds[i] for i in range(len(ds))]).numpy()
+        out[mode + "_rand_after"] = random.random()
+    np.savez_compressed(os.path.join(OUT, "dataset.npz"), segments=np.array(DATASET_SEGMENTS), **out)
+    print("dataset:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
@@ -195,6 +221,8 @@ def main():
         return chinchess_case()
     if "--only-evaluation" in sys.argv:
         return evaluation_case()
+    if "--only-dataset" in sys.argv:
+        return dataset_case()
     encoder_case("kl_f8_seed0_2x64x96_white", 0, (2, 64, 96), 1234, False)
     encoder_case("kl_f8_seed1_1x128x128_smooth", 1, (1, 128, 128), 1234, True)
     encoder_case("kl_f8_seed0_2x256x256_white", 0, (2, 256, 256), 1234, False)      # BASELINE config 1 shape
@@ -206,6 +234,7 @@ def main():
     resize_case()
     chinchess_case()
     evaluation_case()
+    dataset_case()
 
 
 if __name__ == "__main__":

@@ -111,3 +111,20 @@ def embedding_matching_functions(flags=()):
         if isinstance(node, ast.FunctionDef) and node.name in want:
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns
+
+
+def train_dataset_class():
+    """The reference's ``ShuffledStatePairDataset`` (models/percep_RBVAE/percep_RBVAE_train.py:181-360),
+    UNMODIFIED, cut out of the training script with ``ast`` (the script runs a wandb sweep at import)."""
+    import ast
+    import random
+    from pathlib import Path
+    import numpy as np
+    import torch
+    from torch.utils.data import Dataset
+    path = os.path.join(REF_ROOT, "models/percep_RBVAE/percep_RBVAE_train.py")
+    ns = {"torch": torch, "np": np, "random": random, "Path": Path, "Dataset": Dataset}
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.ClassDef) and node.name == "ShuffledStatePairDataset":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns["ShuffledStatePairDataset"]

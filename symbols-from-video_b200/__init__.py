@@ -18,8 +18,9 @@ from ._lib import SfvError, lib
 from .autoencoder import (SCALE_FACTOR, KL_F8_DDCONFIG, AutoencoderKL, DiagonalGaussianDistribution,
                           FirstStage, encoder_param_shapes)
 from .rbvae import Seq2SeqBinaryVAE, hamming_matrix, unpack_codes
-from .pipeline import (EncodeResult, FramePipeline, all_gather_ragged, encode_sharded, load_embeddings_npy,
-                       lookup_embedding, save_embeddings_npy, shard_range)
+from .pipeline import EncodeResult, FramePipeline, all_gather_ragged, encode_sharded, shard_range
+from .embedding_store import (FlatEmbeddingStore, ShuffledStatePairDataset, frame_key, load_embeddings_npy,
+                              lookup_embedding, save_embeddings_npy)
 from . import evaluation, ops
 from .evaluation import (add_gaussian_noise, add_occlusion, assign_label, calculate_state_consistency,
                          labels_from_flags, perturb_frames, state_consistency)

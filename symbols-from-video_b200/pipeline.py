@@ -135,26 +135,3 @@ def encode_sharded(pipe: FramePipeline, frames, rank: int, world: int, gather=Tr
     codes = all_gather_ragged(res.codes.to(dev), counts, group) if res.codes is not None else None
     h = all_gather_ragged(res.h.to(dev), counts, group) if res.h is not None else None
     return EncodeResult(lat, codes, h), (lo, hi)
-
-
-# ---- embedding store: the on-disk format between precompute and training ----
-def save_embeddings_npy(path: str, keys: list[str], latents: torch.Tensor | np.ndarray):
-    """Bit-compatible with get_percep_embeddings.py:106,113: np.save of a pickled
-    dict {basename: float32 ndarray (1,4,h,w)}."""
-    lat = latents.detach().cpu().numpy() if isinstance(latents, torch.Tensor) else latents
-    emb = {k: np.ascontiguousarray(lat[i:i + 1]).astype(np.float32) for i, k in enumerate(keys)}
-    np.save(path, emb)
-
-
-def load_embeddings_npy(path: str) -> dict:
-    """percep_RBVAE_train.py:204: np.load(path, allow_pickle=True).item()."""
-    return np.load(path, allow_pickle=True).item()
-
-
-def lookup_embedding(emb: dict, index: int) -> np.ndarray:
-    """percep_RBVAE_train.py:337-360 `_load_embedding`: key with and without '.jpg'."""
-    base = f"{index:010d}"
-    for k in (base + ".jpg", base):
-        if k in emb:
-            return emb[k]
-    raise KeyError(f"No embedding found for frame index {index}")

@@ -14,7 +14,7 @@ import torch
 import sfv_b200
 from oracle import kl_f8, rbvae as orb
 
-from conftest import ROOT
+from conftest import GOLDEN, ROOT
 
 
 def header_symbols():
@@ -193,3 +193,50 @@ def test_product_weight_and_frame_generators_match_the_oracles():
     from oracle import frames
     assert np.array_equal(sfv_b200.synthetic_frames(2, 32, 40, 9, smooth=True).numpy(),
                           frames.synthetic_frames(2, 32, 40, 9, smooth=True))
+
+
+def _toy_embeddings(n=160, hw=(2, 3), seed=9):
+    # same construction as oracle/make_golden.py:dataset_embeddings (kept literal here: host test, no oracle import needed)
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(n, 4, *hw, generator=g).numpy()
+    return {(f"{i:010d}.jpg" if i % 3 else f"{i:010d}"): lat[i:i + 1] for i in range(n)}
+
+
+def test_flat_embedding_store_round_trip(tmp_path):
+    emb = _toy_embeddings(20)
+    flat = sfv_b200.FlatEmbeddingStore.from_pickled(emb)
+    flat.save(tmp_path / "emb_flat")
+    back = sfv_b200.FlatEmbeddingStore.load(tmp_path / "emb_flat")
+    assert back.keys == list(emb.keys()) and len(back) == 20
+    assert isinstance(back.latents, np.memmap)
+    for i in (0, 1, 7, 19):
+        assert np.array_equal(back.get(i), sfv_b200.lookup_embedding(emb, i))
+    again = back.to_pickled()
+    assert all(np.array_equal(again[k], emb[k]) and again[k].dtype == np.float32 and again[k].shape == (1, 4, 2, 3)
+               for k in emb)
+    # and through the reference's pickled format on disk
+    sfv_b200.save_embeddings_npy(str(tmp_path / "emb.npy"), list(emb.keys()), np.concatenate(list(emb.values())))
+    flat2 = sfv_b200.FlatEmbeddingStore.from_pickled(str(tmp_path / "emb.npy"))
+    assert np.array_equal(np.asarray(flat2.latents), np.asarray(flat.latents))
+    with pytest.raises(KeyError):
+        back.get(20)
+
+
+@pytest.mark.parametrize("mode", ["train", "val", "test"])
+def test_resident_pair_dataset_matches_reference_golden(mode):
+    """tests/golden/dataset.npz: the reference's ShuffledStatePairDataset under random.seed(31)."""
+    import random
+    g = np.load(os.path.join(GOLDEN, "dataset.npz"))
+    segs = [tuple(int(v) for v in s) for s in g["segments"]]
+    random.seed(31)
+    ds = sfv_b200.ShuffledStatePairDataset(_toy_embeddings(), segs, test_pct=0.15, val_pct=0.1, mode=mode, device="cpu")
+    assert random.random() == float(g[mode + "_rand_after"])          # consumed the RNG exactly like the reference
+    assert len(ds) == g[mode + "_items"].shape[0]
+    pairs = np.array([[list(p[i % len(p)]) for p in ds.pairs_per_state] for i in range(len(ds))])
+    assert np.array_equal(pairs, g[mode + "_pairs"])
+    items = torch.stack([ds[i] for i in range(len(ds))]).numpy()
+    assert np.array_equal(items, g[mode + "_items"])
+    assert np.array_equal(ds.batch(list(range(len(ds)))).numpy(), g[mode + "_items"])
+    assert np.array_equal(ds._load_embedding(5).numpy(), _toy_embeddings()["0000000005.jpg"][0])
+    with pytest.raises(ValueError):
+        sfv_b200.ShuffledStatePairDataset(_toy_embeddings(), segs, mode="bogus", device="cpu")

@@ -248,3 +248,33 @@ def test_evaluation_oracle_matches_live_reference():
     x = random.randint(0, 24 - s); y = random.randint(0, 16 - s)
     assert np.array_equal(oev.occlusion_u8(im, x, y, s), ref)
     assert [ns["assign_label"](i, [4, 9]) for i in (0, 3, 4, 8, 9, 100)] == [0, 0, 1, 1, 2, 2]
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_resident_pair_dataset_matches_live_reference():
+    """sfv_b200.ShuffledStatePairDataset (HBM-resident mirror) vs the reference class, other seed/segments."""
+    import random
+    import sfv_b200
+    from oracle.make_golden import dataset_embeddings
+    cls = ref_shim.train_dataset_class()
+    emb = dataset_embeddings(90, (3, 2), seed=4)
+    segs = [(0, 20), (20, 21), (21, 64), (64, 90)]
+    for mode in ("train", "test"):
+        random.seed(77)
+        ref = cls(emb, segs, test_pct=0.2, val_pct=0.2, mode=mode)
+        ref_items = torch.stack([ref[i] for i in range(len(ref))]) if mode == "train" else None
+        after = random.random()
+        random.seed(77)
+        if mode == "test":
+            # the one-frame state has no test frames: the reference raises from __getitem__, so does the mirror
+            ours = sfv_b200.ShuffledStatePairDataset(emb, segs, test_pct=0.2, val_pct=0.2, mode=mode, device="cpu")
+            assert ours.pairs_per_state == ref.pairs_per_state
+            with pytest.raises(ValueError):
+                ref[0]
+            with pytest.raises(ValueError):
+                ours[0]
+            continue
+        ours = sfv_b200.ShuffledStatePairDataset(emb, segs, test_pct=0.2, val_pct=0.2, mode=mode, device="cpu")
+        assert random.random() == after
+        assert ours.pairs_per_state == ref.pairs_per_state
+        assert torch.equal(torch.stack([ours[i] for i in range(len(ours))]), ref_items)
