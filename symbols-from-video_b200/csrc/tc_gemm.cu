@@ -30,6 +30,20 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 x 16-bit = 128 B = one swizzle row
 constexpr unsigned long long kWatchdogCycles = 4000000000ull;  // ~2 s
 
+// Division by a launch-constant divisor without the ~150-cycle IDIV sequence (round-up method of
+// Granlund & Montgomery): q = (umulhi(n, mul) + n) >> shr, exact for 0 <= n < 2^31.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __device__ __forceinline__ int div(int n) const { return (int)((__umulhi((uint32_t)n, mul) + (uint32_t)n) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = (uint32_t)d; f.shr = 0;
+  while ((1u << f.shr) < (uint32_t)d) ++f.shr;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.shr) - (uint64_t)d)) / (uint64_t)d + 1);
+  return f;
+}
+
 struct TcParams {
   int dim_x, dim_y, dim_n;
   int ntaps, kchunks;
@@ -38,6 +52,7 @@ struct TcParams {
   int b_batched;
   int BW_log2, BW, BH;
   int tiles_x, tiles_y, n_tiles_m, n_tiles_n, n_tiles, n_units;
+  FastDiv fd_ntn, fd_tx, fd_ty;        // n_tiles_n, tiles_x, tiles_y
   int Wo, Ho, Cout, n_img;
   float alpha;
   const float* bias;
@@ -55,6 +70,20 @@ struct TcParams {
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
 };
+
+// unit -> (n_tile, m_tile, tx, ty, img) with multiply-shift divisions
+struct TileCoord { int n_tile, m_tile, tx, ty, img; };
+template <int NCTA>
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int unit, int rank) {
+  TileCoord t;
+  int um;
+  p.fd_ntn.divmod(unit, um, t.n_tile);
+  t.m_tile = um * NCTA + rank;
+  int q;
+  p.fd_tx.divmod(t.m_tile, q, t.tx);
+  p.fd_ty.divmod(q, t.img, t.ty);
+  return t;
+}
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -470,11 +499,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       bool ok = true;
       unsigned long long t_wait = 0, t_start = clock64();
       for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
-        const int n_tile = unit % p.n_tiles_n;
-        const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;   // may be a phantom tile (>= n_tiles_m): all OOB -> zeros
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int img = m_tile / (p.tiles_x * p.tiles_y);
+        const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);   // m_tile may be a phantom tile (>= n_tiles_m): all OOB -> zeros
+        const int n_tile = tc.n_tile, m_tile = tc.m_tile, tx = tc.tx, ty = tc.ty, img = tc.img;
         int base[5] = {0, 0, 0, 0, 0};
         if (p.dim_x >= 0) base[p.dim_x] += tx * p.BW;
         if (p.dim_y >= 0) base[p.dim_y] += ty * p.BH;
@@ -667,18 +693,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
     uint8_t* h16_w = epi_h16 + ew * (2 * 2048);
     uint64_t* res_bar_w = res_bar + ew * 3;
-    auto issue_residual = [&](int g) {      // whole warp calls; one elected lane issues
+    auto issue_residual = [&](int g, int slot) {      // whole warp calls; one elected lane issues; slot == g % kResBufs
       const int seq = g / kNChunk, c = g - seq * kNChunk;
       const int unit = unit0 + seq * unit_step;
       if (unit >= p.n_units) return;
-      const int n_tile = unit % p.n_tiles_n;
-      const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
-      const int col0 = n_tile * BLOCK_N + cbase + c * 32;
-      if (m_tile >= p.n_tiles_m || col0 >= p.Cout) return;     // consumer skips the same chunks
-      const int tx = m_tile % p.tiles_x;
-      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-      const int img = m_tile / (p.tiles_x * p.tiles_y);
-      const int slot = g % kResBufs;
+      const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);
+      const int col0 = tc.n_tile * BLOCK_N + cbase + c * 32;
+      if (tc.m_tile >= p.n_tiles_m || col0 >= p.Cout) return;     // consumer skips the same chunks
+      const int tx = tc.tx, ty = tc.ty, img = tc.img;
       if (elect_one_sync()) {
         const uint32_t bar = smem_u32(&res_bar_w[slot]);
         mbar_arrive_expect_tx(bar, 4096);
@@ -687,17 +709,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     };
     int g_cur = 0;                          // global chunk counter of this warp
+    int rslot = 0; uint32_t rphase = 0;     // g_cur % kResBufs and (g_cur / kResBufs) & 1, kept incrementally
     if (use_tma && has_res) {
-      for (int g = 0; g < kResBufs - 1; ++g) issue_residual(g);
+      for (int g = 0; g < kResBufs - 1; ++g) issue_residual(g, g);
     }
     for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
       const unsigned long long t_top = p.dbg ? clock64() : 0;
-      const int n_tile = unit % p.n_tiles_n;
-      const int m_tile = (unit / p.n_tiles_n) * NCTA + (int)rank;
+      const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);
+      const int n_tile = tc.n_tile, m_tile = tc.m_tile, tx = tc.tx, ty = tc.ty, img = tc.img;
       const bool tile_ok = m_tile < p.n_tiles_m;
-      const int tx = m_tile % p.tiles_x;
-      const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-      const int img = m_tile / (p.tiles_x * p.tiles_y);
       const int x = tx * p.BW + xx, y = ty * p.BH + yy;
       const bool row_ok = tile_ok && (x < p.Wo) && (y < p.Ho);
       const long long row_off = (((long long)img * p.Ho + y) * p.Wo + x) * p.ldo;
@@ -721,18 +741,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
           const int sw16 = (lane >> 1) & 3;        // 64B swizzle:  chunk j of row r lives at j ^ ((r >> 1) & 3)
 #pragma unroll (kRegStats ? 2 : 1)
-          for (int c = 0; c < kNChunk; ++c, ++g_cur) {
+          for (int c = 0; c < kNChunk; ++c, ++g_cur, rslot = (rslot + 1 == kResBufs) ? 0 : rslot + 1, rphase ^= (rslot == 0)) {
             const int c0 = c * 32;                              // column inside this warp's share
             const int col0 = n_tile * BLOCK_N + cbase + c0;
             const bool chunk_ok = tile_ok && col0 < p.Cout;     // warp-uniform
             uint32_t v[32];
             tmem_ld32(t_row + cbase + c0, v);
-            const int slot = kResBufs ? g_cur % kResBufs : 0;
+            const int slot = kResBufs ? rslot : 0;
             uint8_t* fb = f32_w + slot * 4096 + lane * 128;
             float f[32];
             unsigned long long tq = p.dbg ? clock64() : 0;
             if (has_res && chunk_ok) {
-              ok = mbar_wait(smem_u32(&res_bar_w[slot]), (uint32_t)((g_cur / kResBufs) & 1), abort_flag, p.err, 5);
+              ok = mbar_wait(smem_u32(&res_bar_w[slot]), rphase, abort_flag, p.err, 5);
               if (!ok) break;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -802,7 +822,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (elect_one_sync()) tma_store_wait_read<1>();
                 __syncwarp();
               }
-              issue_residual(g_cur + kResBufs - 1);   // refills the slot freed by the wait above
+              issue_residual(g_cur + kResBufs - 1, slot == 0 ? kResBufs - 1 : slot - 1);   // refills the slot freed by the wait above
             }
           }
           if (!ok) break;
@@ -1070,6 +1090,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_tiles_n = ceil_div(a.Cout, a.block_n);
   p.n_tiles = p.n_tiles_m * p.n_tiles_n;
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
+  p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
   p.epi_mode = g_epi_mode;
   p.dbg = g_dbg;
   p.a2_kchunks = a.a2 ? a.a2_cin / 64 : 0; p.a2_k0 = a.a2_k0;

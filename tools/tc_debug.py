@@ -5,10 +5,10 @@ os.environ["SFV_TC_DEBUG"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, bench, sfv_b200
-from oracle import frames
+
 vae, rb, sd, rsd = bench.build_models("bf16")
 pipe = sfv_b200.FramePipeline(vae, rb, batch=8)
-u8 = torch.from_numpy(frames.synthetic_frames(8, 512, 512, 1234, smooth=True)).cuda()
+u8 = sfv_b200.synthetic_frames(8, 512, 512, 1234, smooth=True).cuda()
 for i in range(3):
     sys.stderr.write(f"==== pass {i}\n")
     pipe.encode_device(u8)
