@@ -66,6 +66,7 @@ struct TcParams {
   int epi_mode;
   int halo_base_offset;
   int num_stages, res_bufs, h16_slots;   // shared-memory plan of this launch
+  int res_prefetch;                    // L2-prefetch the residual one tile ahead of its TMA load
   int a2_kchunks, a2_k0;               // fused 1x1 branch: extra k-chunks read through the second A map
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
@@ -171,6 +172,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a tile (no shared memory, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 // shared -> global tile store (clips out-of-bounds elements); completion tracked by bulk groups
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -691,7 +697,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_res = p.residual != nullptr;
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
     uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
-    uint8_t* h16_w = epi_h16 + ew * (2 * 2048);
+    uint8_t* h16_w = epi_h16 + ew * (p.h16_slots * 2048);
+    // a staging slot is rewritten (by the next chunk's math or the next residual load) one chunk after the bulk
+    // store that reads it was committed, unless its ring has a single slot: then wait for that store right away
+    const bool deep_rings = (kResBufs == 0 || kResBufs >= 2) && (p.h16_slots == 0 || p.h16_slots >= 2);
     uint64_t* res_bar_w = res_bar + ew * 3;
     auto issue_residual = [&](int g, int slot) {      // whole warp calls; one elected lane issues; slot == g % kResBufs
       const int seq = g / kNChunk, c = g - seq * kNChunk;
@@ -701,17 +710,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col0 = tc.n_tile * BLOCK_N + cbase + c * 32;
       if (tc.m_tile >= p.n_tiles_m || col0 >= p.Cout) return;     // consumer skips the same chunks
       const int tx = tc.tx, ty = tc.ty, img = tc.img;
+      // the ring is only 1-2 chunks deep (shared memory goes to the operand pipeline), which would expose the
+      // full DRAM latency of a tensor written two launches ago: pull the chunk one tile further ahead into L2
+      const int unit_pf = unit + unit_step;
+      const TileCoord tp = tile_coord<NCTA>(p, unit_pf < p.n_units ? unit_pf : unit, (int)rank);
+      const bool pf_ok = p.res_prefetch && unit_pf < p.n_units && tp.m_tile < p.n_tiles_m;
       if (elect_one_sync()) {
         const uint32_t bar = smem_u32(&res_bar_w[slot]);
         mbar_arrive_expect_tx(bar, 4096);
         tma_load_4d(smem_u32(f32_w + slot * 4096), &tmR, bar, col0, tx * p.BW + wx, ty * p.BH + wy, img);
+        if (pf_ok)
+          tma_prefetch_4d(&tmR, tp.n_tile * BLOCK_N + cbase + c * 32, tp.tx * p.BW + wx, tp.ty * p.BH + wy, tp.img);
       }
       __syncwarp();
     };
     int g_cur = 0;                          // global chunk counter of this warp
     int rslot = 0; uint32_t rphase = 0;     // g_cur % kResBufs and (g_cur / kResBufs) & 1, kept incrementally
     if (use_tma && has_res) {
-      for (int g = 0; g < kResBufs - 1; ++g) issue_residual(g, g);
+      for (int g = 0; g < (kResBufs > 1 ? kResBufs - 1 : 1); ++g) issue_residual(g, g);
     }
     for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
       const unsigned long long t_top = p.dbg ? clock64() : 0;
@@ -793,7 +809,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   *reinterpret_cast<float4*>(fb + ((j ^ sw) << 4)) =
                       make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
               }
-              uint8_t* hb = h16_w + (g_cur & 1) * 2048 + lane * 64;
+              const int hslot = p.h16_slots == 2 ? (g_cur & 1) : 0;
+              uint8_t* hb = h16_w + hslot * 2048 + lane * 64;
               if (p.out_16) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -810,19 +827,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (elect_one_sync()) {
                 const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
                 if (p.out_f32) tma_store_4d(&tmO32, smem_u32(f32_w + slot * 4096), col0, ox, oy, img);
-                if (p.out_16) tma_store_4d(&tmO16, smem_u32(h16_w + (g_cur & 1) * 2048), col0, ox, oy, img);
+                if (p.out_16) tma_store_4d(&tmO16, smem_u32(h16_w + hslot * 2048), col0, ox, oy, img);
                 tma_store_commit();
-                tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
+                if (deep_rings) tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
+                else tma_store_wait_read<0>();
               }
               __syncwarp();
               if (p.dbg) { const unsigned long long t1 = clock64(); t_e[3] += t1 - tq; tq = t1; }
             }
             if (has_res) {
               if (!chunk_ok) {                 // skipped chunk: still make sure the slot about to be refilled is free
-                if (elect_one_sync()) tma_store_wait_read<1>();
+                if (elect_one_sync()) { if (deep_rings) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
                 __syncwarp();
               }
-              issue_residual(g_cur + kResBufs - 1, slot == 0 ? kResBufs - 1 : slot - 1);   // refills the slot freed by the wait above
+              issue_residual(g_cur + (kResBufs > 1 ? kResBufs - 1 : 1),
+                             kResBufs > 1 ? (slot == 0 ? kResBufs - 1 : slot - 1) : 0);   // refills the slot freed by the wait above
             }
           }
           if (!ok) break;
@@ -939,6 +958,8 @@ int* g_err_flag = nullptr;
 int g_num_sms = 0;
 int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
 int g_halo = 2;         // SFV_HALO=0 disables the shared A halo box; 2 also uses it for BLOCK_N = 256 (2-stage pipeline)
+int g_epi_slots_auto = 1, g_epi_slots_r = -1, g_epi_slots_h = -1;   // SFV_EPI_SLOTS=auto|fixed|r,h
+int g_res_prefetch = 0;  // SFV_RES_PREFETCH=1: L2-prefetch residual chunks one tile ahead (measured slower: 571->561 us off)
 int g_halo_boff = 0;    // descriptor base-offset for the shifted taps: measured WRONG on B200 (the swizzle is a function of
                         // the absolute smem address bits), so it stays 0; SFV_HALO_BOFF=1 reproduces the failing variant
 int g_epi_mode = 1;
@@ -960,6 +981,11 @@ int tc_init() {
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
   if (const char* e = getenv("SFV_HALO")) g_halo = atoi(e);
   if (const char* e = getenv("SFV_HALO_BOFF")) g_halo_boff = atoi(e);
+  if (const char* e = getenv("SFV_RES_PREFETCH")) g_res_prefetch = atoi(e);
+  if (const char* e = getenv("SFV_EPI_SLOTS")) {
+    if (!strcmp(e, "fixed")) g_epi_slots_auto = 0;
+    else if (strcmp(e, "auto")) sscanf(e, "%d,%d", &g_epi_slots_r, &g_epi_slots_h);
+  }
   if (const char* e = getenv("SFV_TC_DEBUG")) { if (atoi(e)) SFV_CUDA(cudaMalloc(&g_dbg, 8 * 16 * 256)); }
   g_encode = (EncodeTiledFn)fn;
   return 0;
@@ -998,8 +1024,29 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   TcParams p = p_in;
   const bool need_f32 = p.epi_mode == 1 && (p.residual || p.out_f32);
   const bool need_h16 = p.epi_mode == 1 && p.out_16;
+  // Staging depth vs pipeline depth.  Preferred: deep epilogue rings (residual prefetched 1-2 chunks ahead, stores
+  // overlapped).  A HALO stage holds three k-chunks (up to 65 KB), so deep rings can leave only two stages and the
+  // MMA warp starves; when the epilogue has slack (>= ~2000 tensor-pipe cycles per 32-column chunk, 4000 when a
+  // residual load sits in the chain) single-slot rings buy the third stage instead (measured: 448 -> 379 us on the
+  // 512->512 conv2 at 128x128, but 513 -> 551 us on the 256->256 one, hence the threshold).
   p.h16_slots = need_h16 ? 2 : 0;
   p.res_bufs = !need_f32 ? 0 : ((C::kSets == 2 && need_h16) ? 2 : 3);
+  {
+    const int want = HALO ? 3 : 4;
+    const long long k_chunks_total = (long long)p.ntaps * p.kchunks + p.a2_kchunks;
+    constexpr int chunks_per_warp = BLOCK_N >= 32 ? BLOCK_N / C::kSets / 32 : 1;
+    const long long chunk_budget = k_chunks_total * (BLOCK_N * kBlockM * kBlockK / 4096) / chunks_per_warp;
+    if (C::stages_for(p.res_bufs, p.h16_slots) < want && chunk_budget >= (p.residual ? 4000 : 2000) && g_epi_slots_auto) {
+      const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+      for (int i = 0; i < 4; ++i) {
+        const int r = need_f32 ? cand[i][0] : 0, h = need_h16 ? cand[i][1] : 0;
+        if (r > p.res_bufs || h > p.h16_slots) continue;
+        if (C::stages_for(r, h) >= want) { p.res_bufs = r; p.h16_slots = h; break; }
+      }
+    }
+    if (g_epi_slots_r >= 0 && need_f32) p.res_bufs = g_epi_slots_r;       // SFV_EPI_SLOTS=r,h experiment override
+    if (g_epi_slots_h >= 0 && need_h16) p.h16_slots = g_epi_slots_h;
+  }
   p.num_stages = C::stages_for(p.res_bufs, p.h16_slots);
   SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
   const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots);
@@ -1024,8 +1071,8 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     double a[16] = {0}; int n = 0;
     for (int b = 0; b < grid; b += NCTA) { for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k]; ++n; }
     for (int k = 0; k < 16; ++k) a[k] /= n;
-    fprintf(stderr, "TCDBG %s | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f [res_wait %.0f tmem %.0f fence %.0f store %.0f | tile_pre %.0f tile_post %.0f | fma %.0f stats %.0f pack_sts %.0f]\n",
-            tag, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
+    fprintf(stderr, "TCDBG %s st=%d r=%d h=%d | tiles/cta %.1f | producer total %.0f wait_empty %.0f | mma total %.0f wait_full %.0f wait_tempty %.0f | epi total %.0f wait_tfull %.0f [res_wait %.0f tmem %.0f fence %.0f store %.0f | tile_pre %.0f tile_post %.0f | fma %.0f stats %.0f pack_sts %.0f]\n",
+            tag, p.num_stages, p.res_bufs, p.h16_slots, (double)p.n_units / (grid / NCTA), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
   }
   return 0;
 }
@@ -1092,6 +1139,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
   p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
   p.epi_mode = g_epi_mode;
+  p.res_prefetch = g_res_prefetch;
   p.dbg = g_dbg;
   p.a2_kchunks = a.a2 ? a.a2_cin / 64 : 0; p.a2_k0 = a.a2_k0;
   p.halo_base_offset = g_halo_boff;
