@@ -45,36 +45,73 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed regions: NVML every 20 ms (nvidia-smi subprocess fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         super().__init__(daemon=True)
-        self.idx, self.rows, self.stop_flag = gpu_index, [], False
+        self.idx, self.stop_flag = gpu_index, False
+        self.sm, self.mx, self.reasons, self.power, self.source = [], [], set(), [], "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            self.h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) >= 9:
+            self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(self.rows))
+        sm = sorted(self.sm)
+        out = dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                   reasons=sorted(self.reasons), samples=len(sm), source=self.source)
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def build_models(precision):
@@ -211,7 +248,7 @@ def main():
     vae.check_async_error()
 
     # ---- timed: device-resident inputs ---------------------------------------
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None))
     sampler.start()
     lib.sfv_profile_enable(1)
     launches0 = lib.sfv_launch_count()

@@ -16,11 +16,11 @@ def one(B=8, R=512, prec="bf16"):
     import torch
     import bench
     import sfv_b200
-    from oracle import frames
+
     bench.R = R
     vae, rb, sd, rsd = bench.build_models(prec)
     pipe = sfv_b200.FramePipeline(vae, rb, batch=B)
-    u8 = torch.from_numpy(frames.synthetic_frames(B, R, R, 1234, smooth=True)).cuda()
+    u8 = sfv_b200.synthetic_frames(B, R, R, 1234, smooth=True).cuda()
     for _ in range(2):
         r = pipe.encode_device(u8)
     torch.cuda.synchronize()

@@ -9,7 +9,6 @@ import torch
 
 import bench
 import sfv_b200
-from oracle import frames
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -17,14 +16,13 @@ R = int(sys.argv[3]) if len(sys.argv) > 3 else 512
 bench.R = R
 vae, rb, sd, rsd = bench.build_models(prec)
 if R != 512:
-    from oracle import rbvae as orb
     fh = R // 8
     for _ in range(3):
         fh = (fh - 1) // 2 + 1
     rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, input_hw=(R // 8, R // 8))
-    rb.load_state_dict(orb.init_state_dict(4, 25, (fh, fh), seed=1))
+    rb.load_state_dict(sfv_b200.init_rbvae_state_dict(4, 25, (fh, fh), seed=1))
 pipe = sfv_b200.FramePipeline(vae, rb, batch=B)
-u8 = torch.from_numpy(frames.synthetic_frames(B, R, R, 1234, smooth=True)).cuda()
+u8 = sfv_b200.synthetic_frames(B, R, R, 1234, smooth=True).cuda()
 for _ in range(2):
     pipe.encode_device(u8)
 torch.cuda.synchronize()
