@@ -200,6 +200,11 @@ int sfv_op_conv2d(const float* x_nhwc, const float* host_w_oihw, const float* ho
                   int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                   int32_t ksize, int32_t stride, int32_t pad_lo, int32_t pad_hi,
                   int32_t relu, int32_t precision, void* stream);
+/* conv_in (model.py:383-387,439) fed from uint8 HWC frames with load_img's /255, 2x-1 fused
+ * (get_percep_embeddings.py:67-71): frames uint8 [N,H,W,3] -> y fp32 NHWC [N,H,W,128].
+ * precision 0: CUDA-core kernel; 1/2: the tcgen05 kernel with the exact integer operand 2u-255. */
+int sfv_op_conv_in_u8(const uint8_t* frames, const float* host_w_oihw, const float* host_bias, float* y_nhwc,
+                      int32_t N, int32_t H, int32_t W, int32_t precision, void* stream);
 int sfv_op_group_norm(const float* x_nhwc, const float* gamma, const float* beta, float* y_nhwc,
                       int32_t N, int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu,
                       void* stream);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sfv_perturb_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float,
                                      _P, C.c_int32, _P]),
     "sfv_op_conv2d": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int32] * 11 + [_P]),
+    "sfv_op_conv_in_u8": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "sfv_op_group_norm": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_int32, _P]),
     "sfv_op_attention": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),

@@ -119,6 +119,7 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
   e->fmt = fmt_of_precision(precision);
   if (const char* v = getenv("SFV_FUSED_STATS")) e->fused_stats = atoi(v) != 0;
   if (const char* v = getenv("SFV_FUSE_NIN")) e->fuse_nin = atoi(v) != 0;
+  if (const char* v = getenv("SFV_CONV_IN_TC")) e->conv_in_tc = atoi(v) != 0;
   int st = encoder_build(e, tensors, n_tensors);
   if (st != 0) { e->blob.release(); delete e; return st; }
   *out = e;
@@ -275,6 +276,30 @@ int sfv_op_conv2d(const float* x, const float* host_w, const float* host_b, cons
     }
   }
   if (st == 0 && cudaStreamSynchronize(s) != cudaSuccess) st = fail(SFV_ERR_CUDA, "op_conv2d: %s", cudaGetErrorString(cudaGetLastError()));
+  blob.release();
+  return st;
+}
+
+int sfv_op_conv_in_u8(const uint8_t* frames, const float* host_w, const float* host_b, float* y, int32_t N, int32_t H,
+                      int32_t W, int32_t precision, void* stream) {
+  SFV_TRY(require_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!frames || !host_w || !host_b || !y) return fail(SFV_ERR_INVALID, "op_conv_in_u8: null argument");
+  DeviceBlob blob;
+  ConvW w;
+  const int fmt = fmt_of_precision(precision);
+  int st = make_conv_from_host(blob, host_w, host_b, 128, 3, 3, fmt, false, &w);
+  if (st == 0) {
+    if (precision == SFV_PREC_F32) {
+      st = launch_conv_in(frames, SRC_NHWC_U8, w.w32, w.bias, y, nullptr, N, H, W, s);
+    } else {
+      if (W % 8 != 0 || ((uintptr_t)frames & 3) != 0) st = fail(SFV_ERR_INVALID, "op_conv_in_u8: W %% 8 != 0 or unaligned frames");
+      if (st == 0) st = make_conv_in_u8(blob, host_w, fmt, &w);
+      if (st == 0) st = conv_in_tc(w, fmt, frames, N, H, W, y, nullptr, s);
+      if (st == 0) st = tc_check_device_error(s);
+    }
+  }
+  if (st == 0 && cudaStreamSynchronize(s) != cudaSuccess) st = fail(SFV_ERR_CUDA, "op_conv_in_u8: %s", cudaGetErrorString(cudaGetLastError()));
   blob.release();
   return st;
 }

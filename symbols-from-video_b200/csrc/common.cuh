@@ -196,6 +196,9 @@ struct TcGemmArgs {
   float alpha; const float* bias; const float* residual;
   float* out_f32; void* out_16; int fmt; long long ldo; int relu;
   double* gn_stats; int gn_cpg;      // optional fused GroupNorm partial sums [Nimg][Cout/gn_cpg][2] (pre-zeroed)
+  // conv_in mode: instead of a 16-bit A tensor, uint8 HWC frames [Nimg][Ho][Wo][3]; the producer warp builds the
+  // 3x3x3 patch rows (2u-255, zero padded, duplicated for the hi/lo weight split) straight into the swizzled A tile
+  const unsigned char* u8_src;
 };
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s);
 int tc_check_device_error(cudaStream_t s);   // sync + read the watchdog flag

@@ -19,6 +19,7 @@
 namespace sfv {
 
 // ------------------------------------------------------------------ weights
+static constexpr float kConvInScale = 4096.f;
 static const SfvTensor* find_tensor(const SfvTensor* t, int n, const std::string& name) {
   for (int i = 0; i < n; ++i)
     if (t[i].name && name == t[i].name) return &t[i];
@@ -35,6 +36,12 @@ static uint16_t host_to_16(float v, int fmt) {
   __half h = __float2half_rn(v);
   uint16_t o; memcpy(&o, &h, 2);
   return o;
+}
+
+static float host_from_16(uint16_t b, int fmt) {
+  if (fmt == FMT_BF16) { const uint32_t u = (uint32_t)b << 16; float v; memcpy(&v, &u, 4); return v; }
+  __half h; memcpy(&h, &b, 2);
+  return __half2float(h);
 }
 
 int DeviceBlob::upload(const void* host, size_t bytes, void** out) {
@@ -76,6 +83,24 @@ int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Co
     SFV_TRY(blob.upload(w16.data(), w16.size() * 2, &out->w16));
   }
   return 0;
+}
+
+// uint8-fed tensor-core conv_in: x = (2u-255)/255 exactly, so with A = 2u-255 (an odd integer <= 255 in
+// magnitude: exact in bf16 and fp16, and the zero padding of x stays 0) the layer is A . (w/255).  The weight is
+// split hi + lo so the product keeps ~16 (bf16) / 22 (fp16) mantissa bits; kConvInScale keeps lo out of the
+// fp16 subnormals and is undone by the epilogue's alpha.  w: OIHW [128][3][3][3].
+int make_conv_in_u8(DeviceBlob& blob, const float* w, int fmt, ConvW* out) {
+  std::vector<uint16_t> wt((size_t)128 * 64, 0);
+  for (int o = 0; o < 128; ++o)
+    for (int k = 0; k < 27; ++k) {
+      const int tap = k / 3, c = k % 3;                       // k = (dy*3+dx)*3 + c
+      const double v = (double)w[((size_t)o * 3 + c) * 9 + tap] * (double)kConvInScale / 255.0;
+      const uint16_t hi = host_to_16((float)v, fmt);
+      const uint16_t lo = host_to_16((float)(v - (double)host_from_16(hi, fmt)), fmt);
+      wt[(size_t)o * 64 + k] = hi;
+      wt[(size_t)o * 64 + 27 + k] = lo;
+    }
+  return blob.upload(wt.data(), wt.size() * 2, &out->w16_u8);
 }
 
 static int get_conv(DeviceBlob& blob, const SfvTensor* t, int n, const std::string& name, int Cout,
@@ -145,6 +170,10 @@ int encoder_build(SfvEncoder* e, const SfvTensor* t, int n) {
   const std::string p = pre + "encoder.";
   static const int mult[4] = {1, 2, 4, 4};
   SFV_TRY(get_conv(e->blob, t, n, p + "conv_in", 128, 3, 3, fmt, false, &e->conv_in));
+  if (e->prec != SFV_PREC_F32) {
+    const SfvTensor* w = find_tensor(t, n, p + "conv_in.weight");
+    SFV_TRY(make_conv_in_u8(e->blob, w->host_data, fmt, &e->conv_in));
+  }
   int cin = 128;
   for (int l = 0; l < 4; ++l) {
     const int cout = 128 * mult[l];
@@ -282,6 +311,24 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
     SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
     a.gn_stats = gn_stats; a.gn_cpg = w.Cout / 32;
   }
+  return launch_tc_gemm(a, s);
+}
+
+// conv_in on the tensor pipe, fed from uint8 HWC frames (see the weight preparation in encoder_build)
+int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, int W, float* out_f32, double* gn_stats,
+               cudaStream_t s) {
+  SFV_CHECK(w.w16_u8 != nullptr, "conv_in_tc: no uint8 weights");
+  TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u8_src = u8; a.fmt = fmt;
+  a.BW = 128; a.BH = 1;
+  a.dim_x = a.dim_y = a.dim_n = -1;
+  a.ntaps = 1; a.kchunks = 1; a.tap_k[0] = 0;
+  a.b = w.w16_u8; a.b_rows = 128; a.b_k = 64; a.b_row_stride = 128; a.b_batched = 0;
+  a.Wo = W; a.Ho = H; a.Nimg = N; a.Cout = 128; a.block_n = 128;
+  a.alpha = 1.f / kConvInScale; a.bias = w.bias;
+  a.out_f32 = out_f32; a.ldo = 128;
+  if (gn_stats) { a.gn_stats = gn_stats; a.gn_cpg = 4; }      // caller zeroed the accumulators
   return launch_tc_gemm(a, s);
 }
 
@@ -530,7 +577,10 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     // conv_in straight from the boundary layout (fp32 NCHW or uint8 HWC)
     const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
     if (f.sx()) SFV_CUDA(cudaMemsetAsync(f.sx(), 0, sizeof(double) * 2 * 32 * N, s));
-    SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, f.pl.xa, f.sx(), N, H, W, s));
+    if (tc && src_kind == SRC_NHWC_U8 && e->conv_in.w16_u8 && e->conv_in_tc && W % 8 == 0 && ((uintptr_t)xin & 3) == 0)
+      SFV_TRY(conv_in_tc(e->conv_in, e->fmt, (const unsigned char*)xin, N, H, W, f.pl.xa, f.sx(), s));
+    else
+      SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, f.pl.xa, f.sx(), N, H, W, s));
     SFV_TRY(tap(0, f.pl.xa, H, W));
     float* cur = f.pl.xa; float* oth = f.pl.xb;
     const void* cur_op = tc ? nullptr : (const void*)cur;

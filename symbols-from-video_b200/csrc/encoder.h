@@ -16,12 +16,16 @@ struct ConvW {
   float* w32 = nullptr;    // [ks*ks*Cin][Cout] fp32 (CUDA-core kernel)
   void* w16 = nullptr;     // [cout_pad][ks*ks*Cin] 16-bit, K-major (UMMA B operand)
   float* bias = nullptr;   // [cout_pad]
+  void* w16_u8 = nullptr;  // conv_in only: [128][64] 16-bit, k<27: hi(w*4096/255), 27..53: lo, for the uint8-fed tcgen05 path
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, nin, c2n; bool has_nin = false; };   // c2n: conv2 with nin_shortcut fused along K
 
 int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
                         int fmt, bool want16, ConvW* out);
+int make_conv_in_u8(DeviceBlob& blob, const float* w_oihw, int fmt, ConvW* out);
+int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, int W, float* out_f32, double* gn_stats,
+               cudaStream_t s);
 int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
             double* gn_stats = nullptr, const void* a2_16 = nullptr);
@@ -41,6 +45,7 @@ struct SfvEncoder {
   int prec = 0, fmt = 0, chunk = 16;
   bool fuse_nin = true;        // nin_shortcut folded into conv2's GEMM (tensor-core modes)
   bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
+  bool conv_in_tc = true;      // uint8-fed conv_in on the tensor pipe (tensor-core modes; SFV_CONV_IN_TC=0: CUDA cores)
   sfv::DeviceBlob blob;
   sfv::ConvW conv_in, ds[3], q, k, v, qk, proj, conv_out;
   sfv::ResW down[4][2], mid1, mid2;

@@ -67,6 +67,7 @@ struct TcParams {
   int halo_base_offset;
   int num_stages, res_bufs, h16_slots;   // shared-memory plan of this launch
   int res_prefetch;                    // L2-prefetch the residual one tile ahead of its TMA load
+  const unsigned char* u8_src;         // conv_in mode (see TcGemmArgs::u8_src)
   int a2_kchunks, a2_k0;               // fused 1x1 branch: extra k-chunks read through the second A map
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
@@ -504,6 +505,89 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
       unsigned long long t_wait = 0, t_start = clock64();
+      if constexpr (NCTA == 1 && !HALO && BLOCK_N == 128) {
+        if (p.u8_src) {
+          // ---- conv_in: A rows are built here from the uint8 frame, one k-chunk per tile ----
+          // Row m of the tile = pixel (y, x0+m); k = (dy*3+dx)*3 + c for k < 27 holds 2u-255 of pixel
+          // (y+dy-1, x+dx-1) (0 outside the frame = the reference's zero padding of the normalised image),
+          // k = 27..53 repeats them (the weights are split hi + lo), k = 54..63 are zero.  A lane owns 4 adjacent
+          // pixels: per filter row it needs 18 consecutive bytes, fetched as 6 aligned words.
+          const int W3w = p.Wo * 3 / 4;                       // words per frame row
+          uint32_t wcur[3][6];
+          auto fetch = [&](int unit, uint32_t (&w)[3][6], int& x0, int& y) {
+            const TileCoord tc = tile_coord<NCTA>(p, unit, 0);
+            x0 = tc.tx * 128 + lane * 4; y = tc.ty;
+            const bool tile_ok = unit < p.n_units && tc.m_tile < p.n_tiles_m;
+            const int wi0 = 3 * (x0 >> 2) - 1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int yy = y + r - 1;
+              const bool row_ok = tile_ok && yy >= 0 && yy < p.Ho;
+              const uint32_t* rowp = reinterpret_cast<const uint32_t*>(p.u8_src) + ((long long)tc.img * p.Ho + yy) * W3w;
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const int wi = wi0 + i;
+                w[r][i] = (row_ok && wi >= 0 && wi < W3w) ? __ldg(rowp + wi) : 0u;
+              }
+            }
+          };
+          int x0, y;
+          fetch(unit0, wcur, x0, y);
+          for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+            const TileCoord tc = tile_coord<NCTA>(p, unit, 0);
+            // values of the 3 x 18 bytes this lane's four pixels touch
+            float v[3][18];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int yy = y + r - 1;
+              const bool row_ok = yy >= 0 && yy < p.Ho;
+#pragma unroll
+              for (int i = 0; i < 18; ++i) {
+                const int bi = i + 1;                          // byte 0 of the first word is one byte before pixel x0-1
+                const float u = (float)((wcur[r][bi >> 2] >> (8 * (bi & 3))) & 0xffu);
+                const int xx = x0 - 1 + i / 3;
+                const bool okp = row_ok && xx >= 0 && xx < p.Wo;
+                v[r][i] = okp ? fmaf(u, 2.f, -255.f) : 0.f;
+              }
+            }
+            if (unit + unit_step < p.n_units) fetch(unit + unit_step, wcur, x0, y);   // next tile's bytes in flight
+            else { x0 = 0; y = 0; }
+            const unsigned long long tw = p.dbg ? clock64() : 0;
+            ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
+            if (p.dbg) t_wait += clock64() - tw;
+            if (!ok) break;
+            uint8_t* sa_g = smem + stage * C::kStageBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = lane * 4 + j;
+              uint32_t wd[32];
+#pragma unroll
+              for (int q = 0; q < 27; ++q) {                  // 54 values = 27 packed pairs
+                const int e0 = 2 * q, e1 = 2 * q + 1;
+                const int k0 = e0 < 27 ? e0 : e0 - 27, k1 = e1 < 27 ? e1 : e1 - 27;
+                wd[q] = pack2_16(v[k0 / 9][3 * j + k0 % 9], v[k1 / 9][3 * j + k1 % 9], p.fmt);
+              }
+#pragma unroll
+              for (int q = 27; q < 32; ++q) wd[q] = 0u;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(sa_g + m * 128 + ((c ^ (m & 7)) << 4)) =
+                    make_uint4(wd[4 * c], wd[4 * c + 1], wd[4 * c + 2], wd[4 * c + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one_sync()) {
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              mbar_arrive_expect_tx(fb, C::kBBytes);
+              tma_load_3d(smem_u32(sa_g) + C::kABytes, &tmB, fb, 0, tc.n_tile * BLOCK_N, 0);
+            }
+            __syncwarp();
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          }
+          if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 1] = t_wait; }
+          ok = false;                                          // skip the TMA producer loop below
+        }
+      }
       for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
         const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);   // m_tile may be a phantom tile (>= n_tiles_m): all OOB -> zeros
         const int n_tile = tc.n_tile, m_tile = tc.m_tile, tx = tc.tx, ty = tc.ty, img = tc.img;
@@ -1087,10 +1171,14 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_CHECK(a.block_n <= 256, "tc_gemm: block_n > 256");
   SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
   CUtensorMap ma, mb, ma2;
+  if (a.u8_src)
+    SFV_CHECK(a.block_n == 128 && a.BW == 128 && a.BH == 1 && a.ntaps == 1 && a.kchunks == 1 && !a.a2 && a.Wo % 8 == 0 &&
+                  ((uintptr_t)a.u8_src & 3) == 0 && a.Cout == 128,
+              "tc_gemm: conv_in mode needs 128-pixel row tiles, one k-chunk, Cout 128 and a 4-byte aligned frame");
   // HALO variant: 3x3 stride-1 conv, 128-pixel row-segment tiles, taps ordered row-major with dx = -1,0,+1
-  const bool halo = g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
+  const bool halo = !a.u8_src && g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
                     (a.block_n == 128 || (a.block_n == 256 && g_halo >= 2)) && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
-  {
+  if (!a.u8_src) {
     cuuint64_t dims[5], strides[5]; cuuint32_t box[5];
     for (int i = 0; i < 5; ++i) {
       dims[i] = i < a.a_rank ? a.a_dims[i] : 1;
@@ -1114,15 +1202,17 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   // operand traffic per MMA.  A batched B (attention) must be the same for both tiles of a pair.
   const int tiles_m_per_img = ceil_div(a.Wo, a.BW) * ceil_div(a.Ho, a.BH);
   int ncta = (g_ncta_max >= 2 && a.block_n >= 32 && (!a.b_batched || tiles_m_per_img % 2 == 0) &&
-              tiles_m_per_img * a.Nimg >= 2) ? 2 : 1;
+              tiles_m_per_img * a.Nimg >= 2 && !a.u8_src) ? 2 : 1;
   {
     cuuint64_t dims[3] = {a.b_k, a.b_rows, a.b_batched ? (cuuint64_t)a.Nimg : 1};
     cuuint64_t strides[3] = {2, a.b_row_stride, a.b_batched ? a.b_batch_stride : a.b_row_stride * a.b_rows};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.block_n / ncta), 1};
     SFV_TRY(encode_map(&mb, a.fmt, 3, a.b, dims, strides, box));
   }
+  if (a.u8_src) ma = ma2 = mb;          // unused by the kernel in this mode
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.u8_src = a.u8_src;
   p.dim_x = a.dim_x; p.dim_y = a.dim_y; p.dim_n = a.dim_n;
   p.ntaps = a.ntaps; p.kchunks = a.kchunks;
   for (int t = 0; t < a.ntaps; ++t) {

@@ -31,6 +31,18 @@ def conv2d_nhwc(x, weight, bias, stride=1, pad=(1, 1), residual=None, relu=False
     return y
 
 
+def conv_in_u8(frames, weight, bias, precision="fp32"):
+    """uint8 [N,H,W,3] cuda, conv_in weight [128,3,3,3] / bias [128] -> y fp32 NHWC [N,H,W,128]
+    (= conv3x3(2*u/255-1) + bias)."""
+    _lib.require_cuda(frames, "frames")
+    N, H, W, _ = frames.shape
+    y = torch.empty(N, H, W, 128, dtype=torch.float32, device=frames.device)
+    w = _host_f32(weight); b = _host_f32(bias)
+    _lib.check(_lib.lib().sfv_op_conv_in_u8(_lib.ptr(frames.contiguous()), w.ctypes.data, b.ctypes.data, _lib.ptr(y),
+                                            N, H, W, _lib.PRECISIONS[precision], _lib.stream_ptr()))
+    return y
+
+
 def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=False):
     """x fp32 [N,HW,C] (or [N,H,W,C]) cuda -> same shape."""
     _lib.require_cuda(x, "x")

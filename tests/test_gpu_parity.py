@@ -110,6 +110,11 @@ def test_chinchess_480_frame_code_match(prec):
     print(_c().check_chinchess_video(prec))
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_conv_in_tensor_core(prec):
+    print(_c().check_conv_in_tensor_core(prec))
+
+
 def test_evaluation_kernels_bit_exact():
     print(_c().check_evaluation_kernels())
 

@@ -50,6 +50,7 @@ def plan():
               ("contrastive512/fp32", "check_contrastive_512('fp32')"), ("contrastive512/bf16", "check_contrastive_512('bf16')"),
               ("chinchess/fp32", "check_chinchess_video('fp32')"), ("chinchess/fp16", "check_chinchess_video('fp16')"),
               ("chinchess/bf16", "check_chinchess_video('bf16')"),
+              ("conv_in_tc/fp16", "check_conv_in_tensor_core('fp16')"), ("conv_in_tc/bf16", "check_conv_in_tensor_core('bf16')"),
               ("eval/kernels", "check_evaluation_kernels()"), ("eval/pipeline/fp32", "check_state_consistency_pipeline('fp32')"),
               ("eval/pipeline/bf16", "check_state_consistency_pipeline('bf16')"),
               ("edge", "check_edge_cases()")]
