@@ -74,6 +74,10 @@ struct TcParams {
 };
 
 // unit -> (n_tile, m_tile, tx, ty, img) with multiply-shift divisions
+#ifndef SFV_TC_FINE_DEBUG
+#define SFV_TC_FINE_DEBUG 0
+#endif
+constexpr bool kFineDbg = SFV_TC_FINE_DEBUG != 0;   // per-phase cycle counters inside the epilogue chunk loop (58 CS2R per tile)
 struct TileCoord { int n_tile, m_tile, tx, ty, img; };
 template <int NCTA>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int unit, int rank) {
@@ -192,6 +196,18 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 // order generic-proxy shared-memory writes before async-proxy (TMA) accesses
+// explicit shared-space 128-bit accesses on 32-bit addresses (generic LD/ST cost 64-bit address arithmetic per access)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -375,10 +391,10 @@ __device__ __forceinline__ void epi_stats_chunk(const float* f, bool valid, int 
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int j = 0; j < CPG; ++j) {
-      const float t = valid ? f[g * CPG + j] : 0.f;
+      const float t = f[g * CPG + j];
       s += t; q = fmaf(t, t, q);
     }
-    v[2 * g] = s; v[2 * g + 1] = q;
+    v[2 * g] = valid ? s : 0.f; v[2 * g + 1] = valid ? q : 0.f;      // clipped rows of a partial tile contribute nothing
   }
   int idx;
   const float r = halving_reduce<NV>(v, lane, idx);
@@ -401,15 +417,16 @@ constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias 
 // lane's row.  Used by the 8-warp epilogue, which reduces across lanes once per image instead of once per chunk.
 template <int CPG>
 __device__ __forceinline__ void epi_stats_lane(const float* f, bool valid, float* acc) {
+  if (!valid) return;                     // only lanes of a partial tile's clipped rows diverge here
 #pragma unroll
   for (int g = 0; g < 32 / CPG; ++g) {
-    float s = 0.f, q = 0.f;
+    float s = acc[2 * g], q = acc[2 * g + 1];
 #pragma unroll
     for (int j = 0; j < CPG; ++j) {
-      const float t = valid ? f[g * CPG + j] : 0.f;
+      const float t = f[g * CPG + j];
       s += t; q = fmaf(t, t, q);
     }
-    acc[2 * g] += s; acc[2 * g + 1] += q;
+    acc[2 * g] = s; acc[2 * g + 1] = q;
   }
 }
 
@@ -781,7 +798,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_res = p.residual != nullptr;
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
     uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
+    const uint32_t f32_s = smem_u32(f32_w), bias_s = smem_u32(bias_w);
     uint8_t* h16_w = epi_h16 + ew * (p.h16_slots * 2048);
+    const uint32_t h16_s = smem_u32(h16_w);
     // a staging slot is rewritten (by the next chunk's math or the next residual load) one chunk after the bulk
     // store that reads it was committed, unless its ring has a single slot: then wait for that store right away
     const bool deep_rings = (kResBufs == 0 || kResBufs >= 2) && (p.h16_slots == 0 || p.h16_slots >= 2);
@@ -848,76 +867,74 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld32(t_row + cbase + c0, v);
             const int slot = kResBufs ? rslot : 0;
-            uint8_t* fb = f32_w + slot * 4096 + lane * 128;
+            const uint32_t fb = f32_s + slot * 4096 + lane * 128;
+            const uint32_t bw = bias_s + c0 * 4;
             float f[32];
-            unsigned long long tq = p.dbg ? clock64() : 0;
+            unsigned long long tq = kFineDbg && p.dbg ? clock64() : 0;
             if (has_res && chunk_ok) {
               ok = mbar_wait(smem_u32(&res_bar_w[slot]), rphase, abort_flag, p.err, 5);
               if (!ok) break;
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[0] += t1 - tq; tq = t1; }
+              tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 r4 = *reinterpret_cast<const float4*>(fb + ((j ^ sw) << 4));
-                f[4 * j] = r4.x; f[4 * j + 1] = r4.y; f[4 * j + 2] = r4.z; f[4 * j + 3] = r4.w;
+                const float4 r4 = lds128(fb + ((j ^ sw) << 4));
+                const float4 b4 = lds128(bw + j * 16);
+                f[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.alpha, b4.x) + r4.x;
+                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b4.y) + r4.y;
+                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b4.z) + r4.z;
+                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b4.w) + r4.w;
               }
             } else {
+              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = 0.f;
-            }
-            if (p.dbg) { const unsigned long long t1 = clock64(); t_e[0] += t1 - tq; tq = t1; }
-            tmem_ld_wait();
-            if (p.dbg) { const unsigned long long t1 = clock64(); t_e[1] += t1 - tq; tq = t1; }
-            if (chunk_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_w + c0 + j);
-                f[j] += fmaf(__uint_as_float(v[j]), p.alpha, b.x);
-                f[j + 1] += fmaf(__uint_as_float(v[j + 1]), p.alpha, b.y);
-                f[j + 2] += fmaf(__uint_as_float(v[j + 2]), p.alpha, b.z);
-                f[j + 3] += fmaf(__uint_as_float(v[j + 3]), p.alpha, b.w);
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = lds128(bw + j * 16);
+                f[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.alpha, b4.x);
+                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b4.y);
+                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b4.z);
+                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b4.w);
               }
+            }
+            if (chunk_ok) {
               if (p.relu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
               }
-              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[6] += t1 - tq; tq = t1; }
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[6] += t1 - tq; tq = t1; }
               if (p.gn_stats) {   // statistics of the finished fp32 values (bias and residual included)
                 if (kRegStats && p.gn_cpg == 4) epi_stats_lane<4>(f, row_ok, gacc + (kRegStats ? c * 16 : 0));
                 else if (p.gn_cpg == 4) epi_stats_chunk<4>(f, row_ok, lane, acc_w, c0 / 4);
                 else if (p.gn_cpg == 8) epi_stats_chunk<8>(f, row_ok, lane, acc_w, c0 / 8);
                 else epi_stats_chunk<16>(f, row_ok, lane, acc_w, c0 / 16);
               }
-              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[7] += t1 - tq; tq = t1; }
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[7] += t1 - tq; tq = t1; }
               if (p.out_f32) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  *reinterpret_cast<float4*>(fb + ((j ^ sw) << 4)) =
-                      make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) sts128(fb + ((j ^ sw) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
               }
               const int hslot = p.h16_slots == 2 ? (g_cur & 1) : 0;
-              uint8_t* hb = h16_w + hslot * 2048 + lane * 64;
+              const uint32_t hb = h16_s + hslot * 2048 + lane * 64;
               if (p.out_16) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 u;
-                  u.x = pack2_16(f[8 * j], f[8 * j + 1], p.fmt);     u.y = pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt);
-                  u.z = pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt); u.w = pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt);
-                  *reinterpret_cast<uint4*>(hb + ((j ^ sw16) << 4)) = u;
-                }
+                for (int j = 0; j < 4; ++j)
+                  sts128u(hb + ((j ^ sw16) << 4), pack2_16(f[8 * j], f[8 * j + 1], p.fmt), pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt),
+                          pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt), pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt));
               }
-              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[8] += t1 - tq; tq = t1; }
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[8] += t1 - tq; tq = t1; }
               fence_proxy_async();
               __syncwarp();
-              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
               if (elect_one_sync()) {
                 const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
-                if (p.out_f32) tma_store_4d(&tmO32, smem_u32(f32_w + slot * 4096), col0, ox, oy, img);
-                if (p.out_16) tma_store_4d(&tmO16, smem_u32(h16_w + hslot * 2048), col0, ox, oy, img);
+                if (p.out_f32) tma_store_4d(&tmO32, f32_s + slot * 4096, col0, ox, oy, img);
+                if (p.out_16) tma_store_4d(&tmO16, h16_s + hslot * 2048, col0, ox, oy, img);
                 tma_store_commit();
                 if (deep_rings) tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
                 else tma_store_wait_read<0>();
               }
               __syncwarp();
-              if (p.dbg) { const unsigned long long t1 = clock64(); t_e[3] += t1 - tq; tq = t1; }
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[3] += t1 - tq; tq = t1; }
             }
             if (has_res) {
               if (!chunk_ok) {                 // skipped chunk: still make sure the slot about to be refilled is free
