@@ -262,7 +262,7 @@ def main():
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.sfv_launch_count() - launches0
     prof = {}
-    for cat, name in enumerate(["tc_gemm", "igemm_f32", "gn_stats", "gn_apply", "softmax", "other"]):
+    for cat, name in enumerate(["tc_gemm", "conv_in", "gn_stats", "gn_apply", "softmax", "other"]):
         ms, work, n = C.c_double(), C.c_double(), C.c_int64()
         lib.sfv_profile_read(cat, C.byref(ms), C.byref(work), C.byref(n))
         prof[name] = dict(ms=ms.value, work=work.value, launches=n.value)
@@ -373,9 +373,9 @@ def main():
                       pipeline_tflops=flops_frame * value / world / 1e12 if flops_frame else None,
                       pipeline_frac_of_peak=flops_frame * value / world / 1e12 / peak if flops_frame else None),
         kernel_classes={k: dict(ms_per_step=v["ms"] / args.steps, launches_per_step=v["launches"] / args.steps,
-                                rate=(v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("tc_gemm", "igemm_f32") else 1e9))
+                                rate=(v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("tc_gemm", "conv_in") else 1e9))
                                 if v["ms"] > 0 else None,
-                                rate_unit="TFLOP/s" if k in ("tc_gemm", "igemm_f32") else "GB/s")
+                                rate_unit="TFLOP/s" if k in ("tc_gemm", "conv_in") else "GB/s")
                         for k, v in prof.items()},
         cpu_baseline=cpu, parity=parity, alt_precision=alt)
     print(json.dumps(line), flush=True)

@@ -430,6 +430,45 @@ __device__ __forceinline__ void epi_stats_lane(const float* f, bool valid, float
   }
 }
 
+// conv_in mode, a lane's four adjacent pixels x0 .. x0+3 of row y.
+// conv_in_values: the 3 x 18 bytes around them (6 aligned words per filter row; byte 0 of the first word is one byte
+// before pixel x0-1) -> 2u-255 as floats, 0 outside the frame.  INTERIOR skips the zero-padding selects.
+template <bool INTERIOR>
+__device__ __forceinline__ void conv_in_values(const uint32_t (&w)[3][6], int x0, int y, int W, int H, float (&v)[3][18]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    const bool row_ok = INTERIOR || (yy >= 0 && yy < H);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const int bi = i + 1;
+      const float t = fmaf((float)((w[r][bi >> 2] >> (8 * (bi & 3))) & 0xffu), 2.f, -255.f);
+      if constexpr (INTERIOR) v[r][i] = t;
+      else { const int xx = x0 - 1 + i / 3; v[r][i] = (row_ok && xx >= 0 && xx < W) ? t : 0.f; }
+    }
+  }
+}
+// conv_in_store_rows: rows m0 .. m0+3 of the 128B-swizzled A tile; k = (dy*3+dx)*3+c for k < 27, repeated at 27..53.
+template <int FMT>
+__device__ __forceinline__ void conv_in_store_rows(const float (&v)[3][18], uint32_t tile_s, int m0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int m = m0 + j;
+    const uint32_t row_s = tile_s + m * 128;
+    uint32_t wd[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) {                            // 54 values = 27 packed pairs
+      const int e0 = 2 * i, e1 = 2 * i + 1;
+      const int k0 = e0 < 27 ? e0 : e0 - 27, k1 = e1 < 27 ? e1 : e1 - 27;
+      wd[i] = pack2_16(v[k0 / 9][3 * j + k0 % 9], v[k1 / 9][3 * j + k1 % 9], FMT);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      sts128u(row_s + ((c ^ (m & 7)) << 4), 4 * c < 27 ? wd[4 * c] : 0u, 4 * c + 1 < 27 ? wd[4 * c + 1] : 0u,
+              4 * c + 2 < 27 ? wd[4 * c + 2] : 0u, 4 * c + 3 < 27 ? wd[4 * c + 3] : 0u);
+  }
+}
+
 template <int BLOCK_N, int NCTA, bool HALO = false>
 struct Cfg {
   static constexpr int kGroup = HALO ? 3 : 1;                           // filter taps per pipeline stage
@@ -528,75 +567,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // Row m of the tile = pixel (y, x0+m); k = (dy*3+dx)*3 + c for k < 27 holds 2u-255 of pixel
           // (y+dy-1, x+dx-1) (0 outside the frame = the reference's zero padding of the normalised image),
           // k = 27..53 repeats them (the weights are split hi + lo), k = 54..63 are zero.  A lane owns 4 adjacent
-          // pixels: per filter row it needs 18 consecutive bytes, fetched as 6 aligned words.
+          // pixels: per filter row it needs 18 consecutive bytes = 6 aligned words, loaded in bounds (indices are
+          // clamped; whatever lies outside the frame is masked) one tile ahead: the words are turned into values
+          // first, then the same registers receive the next tile's loads while the rows are packed and stored.
           const int W3w = p.Wo * 3 / 4;                       // words per frame row
-          uint32_t wcur[3][6];
-          auto fetch = [&](int unit, uint32_t (&w)[3][6], int& x0, int& y) {
-            const TileCoord tc = tile_coord<NCTA>(p, unit, 0);
-            x0 = tc.tx * 128 + lane * 4; y = tc.ty;
-            const bool tile_ok = unit < p.n_units && tc.m_tile < p.n_tiles_m;
-            const int wi0 = 3 * (x0 >> 2) - 1;
+          const uint32_t* src32 = reinterpret_cast<const uint32_t*>(p.u8_src);
+          uint32_t w[3][6];
+          auto fetch = [&](const TileCoord& tc) {
+            const int wi0 = 3 * (tc.tx * 32 + lane) - 1;      // word holding the byte before pixel x0-1 (x0 = tx*128 + 4*lane)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-              const int yy = y + r - 1;
-              const bool row_ok = tile_ok && yy >= 0 && yy < p.Ho;
-              const uint32_t* rowp = reinterpret_cast<const uint32_t*>(p.u8_src) + ((long long)tc.img * p.Ho + yy) * W3w;
+              const int yy = min(max(tc.ty + r - 1, 0), p.Ho - 1);
+              const uint32_t* rowp = src32 + ((long long)tc.img * p.Ho + yy) * W3w;
 #pragma unroll
-              for (int i = 0; i < 6; ++i) {
-                const int wi = wi0 + i;
-                w[r][i] = (row_ok && wi >= 0 && wi < W3w) ? __ldg(rowp + wi) : 0u;
-              }
+              for (int i = 0; i < 6; ++i) w[r][i] = __ldg(rowp + min(max(wi0 + i, 0), W3w - 1));
             }
           };
-          int x0, y;
-          fetch(unit0, wcur, x0, y);
+          TileCoord tc = tile_coord<NCTA>(p, unit0 < p.n_units ? unit0 : 0, 0);
+          fetch(tc);
+#pragma unroll 1
           for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
-            const TileCoord tc = tile_coord<NCTA>(p, unit, 0);
-            // values of the 3 x 18 bytes this lane's four pixels touch
+            const int x0 = tc.tx * 128 + 4 * lane, y = tc.ty, n_tile = tc.n_tile;
             float v[3][18];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const int yy = y + r - 1;
-              const bool row_ok = yy >= 0 && yy < p.Ho;
-#pragma unroll
-              for (int i = 0; i < 18; ++i) {
-                const int bi = i + 1;                          // byte 0 of the first word is one byte before pixel x0-1
-                const float u = (float)((wcur[r][bi >> 2] >> (8 * (bi & 3))) & 0xffu);
-                const int xx = x0 - 1 + i / 3;
-                const bool okp = row_ok && xx >= 0 && xx < p.Wo;
-                v[r][i] = okp ? fmaf(u, 2.f, -255.f) : 0.f;
-              }
-            }
-            if (unit + unit_step < p.n_units) fetch(unit + unit_step, wcur, x0, y);   // next tile's bytes in flight
-            else { x0 = 0; y = 0; }
+            const bool interior = __all_sync(0xffffffffu, y >= 1 && y + 1 < p.Ho && x0 >= 1 && x0 + 4 < p.Wo);
+            if (interior) conv_in_values<true>(w, x0, y, p.Wo, p.Ho, v);
+            else conv_in_values<false>(w, x0, y, p.Wo, p.Ho, v);
+            if (unit + unit_step < p.n_units) { tc = tile_coord<NCTA>(p, unit + unit_step, 0); fetch(tc); }
             const unsigned long long tw = p.dbg ? clock64() : 0;
             ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, abort_flag, p.err, 1);
             if (p.dbg) t_wait += clock64() - tw;
             if (!ok) break;
-            uint8_t* sa_g = smem + stage * C::kStageBytes;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int m = lane * 4 + j;
-              uint32_t wd[32];
-#pragma unroll
-              for (int q = 0; q < 27; ++q) {                  // 54 values = 27 packed pairs
-                const int e0 = 2 * q, e1 = 2 * q + 1;
-                const int k0 = e0 < 27 ? e0 : e0 - 27, k1 = e1 < 27 ? e1 : e1 - 27;
-                wd[q] = pack2_16(v[k0 / 9][3 * j + k0 % 9], v[k1 / 9][3 * j + k1 % 9], p.fmt);
-              }
-#pragma unroll
-              for (int q = 27; q < 32; ++q) wd[q] = 0u;
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(sa_g + m * 128 + ((c ^ (m & 7)) << 4)) =
-                    make_uint4(wd[4 * c], wd[4 * c + 1], wd[4 * c + 2], wd[4 * c + 3]);
-            }
+            const uint32_t tile_s = smem_u32(smem + stage * C::kStageBytes);
+            if (p.fmt == FMT_BF16) conv_in_store_rows<FMT_BF16>(v, tile_s, 4 * lane);
+            else conv_in_store_rows<FMT_F16>(v, tile_s, 4 * lane);
             fence_proxy_async();
             __syncwarp();
             if (elect_one_sync()) {
               const uint32_t fb = smem_u32(&full_bar[stage]);
               mbar_arrive_expect_tx(fb, C::kBBytes);
-              tma_load_3d(smem_u32(sa_g) + C::kABytes, &tmB, fb, 0, tc.n_tile * BLOCK_N, 0);
+              tma_load_3d(tile_s + C::kABytes, &tmB, fb, 0, n_tile * BLOCK_N, 0);
             }
             __syncwarp();
             if (++stage == num_stages) { stage = 0; phase ^= 1; }
@@ -1155,7 +1164,8 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   const int grid = (p.n_units < max_units ? p.n_units : max_units) * NCTA;
   // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
   const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
-  ProfScope prof(PROF_TC_GEMM, flops, s, tag);
+  // conv_in (K = 27, write-bound) is accounted with the other first-layer kernels, not with the tensor-bound GEMMs
+  ProfScope prof(p.u8_src ? PROF_IGEMM : PROF_TC_GEMM, flops, s, tag);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
