@@ -323,17 +323,18 @@ int sfv_op_attention(const float* q, const float* k, const float* v, float* out,
   cudaStream_t s = (cudaStream_t)stream;
   Scratch sc;
   void* S = nullptr;
-  SFV_TRY(sc.get((size_t)N * L * L * 4, &S));
+  const size_t Lp = ((size_t)L + 7) / 8 * 8;      // padded row pitch of S / P / V^T in the tensor-core path
+  SFV_TRY(sc.get((size_t)N * L * Lp * 4, &S));
   if (precision == SFV_PREC_F32) {
     SFV_TRY(attention_f32(q, k, v, out, (float*)S, N, L, C, scale, s));
   } else {
     // q, k in 16 bit; V^T through the same swapped-operand GEMM the encoder uses (identity weights)
-    SFV_CHECK(C % 64 == 0 && L % 8 == 0, "op_attention: needs C %% 64 == 0 and L %% 8 == 0");
+    SFV_CHECK(C % 64 == 0, "op_attention: needs C %% 64 == 0");
     const int fmt = fmt_of_precision(precision);
     const long long n = (long long)N * L * C;
     void *q16, *k16, *v16, *vT, *P, *O16;
     SFV_TRY(sc.get(n * 2, &q16)); SFV_TRY(sc.get(n * 2, &k16)); SFV_TRY(sc.get(n * 2, &v16));
-    SFV_TRY(sc.get(n * 2, &vT)); SFV_TRY(sc.get((size_t)N * L * L * 2, &P)); SFV_TRY(sc.get(n * 2, &O16));
+    SFV_TRY(sc.get((size_t)N * C * Lp * 2, &vT)); SFV_TRY(sc.get((size_t)N * L * Lp * 2, &P)); SFV_TRY(sc.get(n * 2, &O16));
     SFV_TRY(launch_f32_to_16(q, q16, n, fmt, s));
     SFV_TRY(launch_f32_to_16(k, k16, n, fmt, s));
     SFV_TRY(launch_f32_to_16(v, v16, n, fmt, s));

@@ -153,7 +153,7 @@ int launch_zero(void* p, size_t bytes, cudaStream_t s);
 int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t s);
 int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s);
 int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,
-                        cudaStream_t s);
+                        cudaStream_t s, long long ld = 0)   /* ld: row pitch of x and y in elements (0 = cols) */;
 int launch_head(const float* moments_nhwc8, float* params, float* logvar, float* stdv, float* var,
                 int N, int HW, cudaStream_t s);
 int launch_sample(const float* mean, const float* logvar, const float* noise, float scale,

@@ -370,13 +370,14 @@ void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
   p->x16b = tc ? ar.take(E0 / 4 * osz) : nullptr;   // 16-bit copy of a downsample output feeding nin_shortcut
   p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   p->stats2 = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
-  const size_t per_img = L * L * (tc ? 6 : 4);
+  const size_t Lp = (L + 7) / 8 * 8;                  // row pitch of S / P / V^T (16-byte rows for TMA)
+  const size_t per_img = L * Lp * (tc ? 6 : 4);
   size_t na = (size_t)(1536ull << 20) / (per_img ? per_img : 1);
   if (na < 1) na = 1;
   if (na > (size_t)Bc) na = Bc;
   p->attn_chunk = (int)na;
-  p->S = (float*)ar.take(na * L * L * 4);
-  p->P = tc ? ar.take(na * L * L * 2) : nullptr;
+  p->S = (float*)ar.take(na * L * Lp * 4);
+  p->P = tc ? ar.take(na * L * Lp * 2) : nullptr;
   p->moments = (float*)ar.take((size_t)Bc * L * 8 * 4);
 }
 
@@ -438,9 +439,9 @@ struct Fwd {
     const float scale = 1.0f / sqrtf((float)C);
     SFV_TRY(gn(e->attn_norm, x, false, L, 0, pl.oa, sx()));       // hn (no SiLU)
     if (tc) {
-      SFV_CHECK(L % 8 == 0, "tensor-core attention needs (H/8)*(W/8) %% 8 == 0 (got %d)", L);
+      const int Lp = (L + 7) / 8 * 8;                       // token counts need not be a multiple of 8: padded row pitch
       uint16_t* qk = (uint16_t*)pl.ob;                      // [N][L][1024]: q | k
-      uint16_t* vT = (uint16_t*)pl.x16;                     // [N][512][L]
+      uint16_t* vT = (uint16_t*)pl.x16;                     // [N][512][Lp]
       SFV_TRY(conv_tc(e->qk, fmt, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s, nullptr));
       // bias b_v is added after P V (rows of P sum to 1)
       SFV_TRY(vT_tc(e->v, fmt, pl.oa, vT, N, L, s));
@@ -448,7 +449,7 @@ struct Fwd {
       for (int n0 = 0; n0 < N; n0 += pl.attn_chunk) {
         const int nn = (N - n0) < pl.attn_chunk ? (N - n0) : pl.attn_chunk;
         SFV_TRY(attention_tc(fmt, qk + (size_t)n0 * L * 1024, 1024, qk + (size_t)n0 * L * 1024 + 512, 1024,
-                             vT + (size_t)n0 * C * L, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
+                             vT + (size_t)n0 * C * Lp, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
                              scale, s));
       }
       SFV_TRY(conv_tc(e->proj, fmt, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s, sx()));
@@ -475,10 +476,11 @@ struct Fwd {
 
 // Tensor-core attention core for a chunk of images whose score matrices fit S/P:
 //   S = scale * Q K^T (fp32) ; P = softmax(S) (16-bit) ; O = P V + b_v (16-bit)
-// q16/k16: [N][L][*] rows with pitch q_ld/k_ld elements; vT16: [N][C][L].
+// q16/k16: [N][L][*] rows with pitch q_ld/k_ld elements; vT16: [N][C][Lp], S/P: [N][L][Lp], Lp = L rounded up to 8.
 int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long long k_ld,
                  const void* vT16, const float* v_bias, float* S, void* P, void* O16, int N, int L, int C,
                  float scale, cudaStream_t s) {
+  const int Lp = (L + 7) / 8 * 8;       // row pitch of S, P and V^T
   {
     TcGemmArgs a; memset(&a, 0, sizeof(a));
     a.a = q16; a.fmt = fmt; a.a_rank = 3;
@@ -490,20 +492,20 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
     a.b = k16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)k_ld * 2;
     a.b_batch_stride = (unsigned long long)L * k_ld * 2; a.b_batched = 1;
     a.BW = 128; a.BH = 1; a.Wo = L; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
-    a.alpha = scale; a.out_f32 = S; a.ldo = L;
+    a.alpha = scale; a.out_f32 = S; a.ldo = Lp;
     SFV_TRY(launch_tc_gemm(a, s));
   }
-  SFV_TRY(launch_softmax_rows(S, P, 1, fmt, (long long)N * L, L, s));
+  SFV_TRY(launch_softmax_rows(S, P, 1, fmt, (long long)N * L, L, s, Lp));
   {
     TcGemmArgs a; memset(&a, 0, sizeof(a));
     a.a = P; a.fmt = fmt; a.a_rank = 3;
     a.a_dims[0] = L; a.a_dims[1] = L; a.a_dims[2] = N;
-    a.a_strides[1] = (unsigned long long)L * 2; a.a_strides[2] = (unsigned long long)L * L * 2;
+    a.a_strides[1] = (unsigned long long)Lp * 2; a.a_strides[2] = (unsigned long long)L * Lp * 2;
     a.a_box[0] = 64; a.a_box[1] = 128; a.a_box[2] = 1;
     a.dim_x = 1; a.dim_y = -1; a.dim_n = 2;
     a.ntaps = 1; a.kchunks = ceil_div(L, 64);
-    a.b = vT16; a.b_rows = C; a.b_k = L; a.b_row_stride = (unsigned long long)L * 2;
-    a.b_batch_stride = (unsigned long long)C * L * 2; a.b_batched = 1;
+    a.b = vT16; a.b_rows = C; a.b_k = L; a.b_row_stride = (unsigned long long)Lp * 2;
+    a.b_batch_stride = (unsigned long long)C * Lp * 2; a.b_batched = 1;
     a.BW = 128; a.BH = 1; a.Wo = L; a.Ho = 1; a.Nimg = N; a.Cout = C; a.block_n = pick_block_n(C);
     a.alpha = 1.f; a.bias = v_bias; a.out_16 = O16; a.ldo = C;
     SFV_TRY(launch_tc_gemm(a, s));
@@ -524,7 +526,7 @@ int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cu
   a.b = x16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)C * 2;
   a.b_batch_stride = (unsigned long long)L * C * 2; a.b_batched = 1;
   a.BW = 128; a.BH = 1; a.Wo = v.Cout; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
-  a.alpha = 1.f; a.out_16 = vT16; a.ldo = L;
+  a.alpha = 1.f; a.out_16 = vT16; a.ldo = (L + 7) / 8 * 8;
   return launch_tc_gemm(a, s);
 }
 

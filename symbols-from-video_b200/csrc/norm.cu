@@ -375,12 +375,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, void*
   }
 }
 
-// any row length (tiny latents in check mode): one warp per row, scalar accesses
-__global__ void softmax_rows_scalar_kernel(const float* x, float* y, long long rows, int cols) {
+// any row length / row pitch (token counts that are not a multiple of 8, tiny latents in check mode):
+// one warp per row, scalar accesses; rows of x have pitch ldx, rows of y pitch ldy (elements)
+__global__ void softmax_rows_scalar_kernel(const float* x, long long ldx, void* y, long long ldy, int y_is16, int fmt,
+                                           long long rows, int cols) {
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* xr = x + r * cols;
+  const float* xr = x + r * ldx;
   float mx = -INFINITY;
   for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -388,7 +390,11 @@ __global__ void softmax_rows_scalar_kernel(const float* x, float* y, long long r
   for (int c = lane; c < cols; c += 32) sum += expf(xr[c] - mx);
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.f / sum;
-  for (int c = lane; c < cols; c += 32) y[r * cols + c] = expf(xr[c] - mx) * inv;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = expf(xr[c] - mx) * inv;
+    if (y_is16) reinterpret_cast<uint16_t*>(y)[r * ldy + c] = (uint16_t)(pack2_16(v, 0.f, fmt) & 0xffffu);
+    else reinterpret_cast<float*>(y)[r * ldy + c] = v;
+  }
 }
 
 // DiagonalGaussian head (distributions.py:24-31): moments NHWC [N,HW,8] ->
@@ -509,11 +515,12 @@ int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t
 }
 
 int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,
-                        cudaStream_t s) {
+                        cudaStream_t s, long long ld) {
   SFV_CHECK(rows < (1ll << 31), "softmax: too many rows");
-  if (cols % 4 != 0) {
-    SFV_CHECK(!y_is16, "softmax: 16-bit output needs cols %% 4 == 0");
-    softmax_rows_scalar_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, (float*)y, rows, cols);
+  if (ld <= 0) ld = cols;
+  if (cols % 4 != 0 || ld != cols) {
+    ProfScope prof(PROF_SOFTMAX, (double)rows * cols * (4 + (y_is16 ? 2 : 4)), s);
+    softmax_rows_scalar_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, ld, y, ld, y_is16, fmt, rows, cols);
     SFV_LAUNCH_OK();
     return 0;
   }

@@ -1194,7 +1194,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_TRY(tc_init());
   SFV_CHECK(a.BW * a.BH == kBlockM && (a.BW & (a.BW - 1)) == 0, "tc_gemm: bad tile %dx%d", a.BW, a.BH);
   SFV_CHECK(a.ntaps >= 1 && a.ntaps <= 9 && a.kchunks >= 1, "tc_gemm: bad taps/kchunks");
-  SFV_CHECK(a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0");
+
   SFV_CHECK(a.block_n <= 256, "tc_gemm: block_n > 256");
   SFV_CHECK(a.ldo % 4 == 0, "tc_gemm: ldo %% 4 != 0");
   CUtensorMap ma, mb, ma2;
@@ -1275,6 +1275,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
                        (!a.out_f32 || ((uintptr_t)a.out_f32 & 15) == 0) && (!a.out_16 || ((uintptr_t)a.out_16 & 15) == 0) &&
                        (!a.residual || ((uintptr_t)a.residual & 15) == 0);
   p.epi_mode = tma_epi ? 1 : 0;
+  SFV_CHECK(tma_epi || a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0 needs the TMA epilogue (ldo %% 8 == 0, aligned outputs)");
   if (tma_epi) {
     const cuuint32_t bx = a.BW < 32 ? a.BW : 32, by = 32 / bx;
     cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.Nimg};

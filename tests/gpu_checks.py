@@ -569,6 +569,23 @@ def check_conv_in_tensor_core(prec="fp16"):
     return out
 
 
+def check_odd_token_count(prec="fp16"):
+    """Frame sizes whose token count (H/8)*(W/8) is not a multiple of 8 (40x200 -> 125 tokens, 8x8 -> 1 token):
+    legal for AutoencoderKL.encode (autoencoder.py:324-328 only needs multiples of 8); the tensor-core attention uses
+    a padded row pitch for S / P / V^T there."""
+    out = {}
+    vae, sd = make_vae(prec, 0)
+    for B, H, W in ((2, 40, 200), (1, 8, 8), (1, 24, 40)):
+        u8 = frames.synthetic_frames(B, H, W, 3 + W, smooth=H > 8)
+        x = frames.normalise_u8(u8)
+        got = vae.encode(x.to(DEV))
+        vae.check_async_error()
+        ref = kl_f8.encode(x, sd)
+        out[f"{B}x{H}x{W}"] = dict(mean=rel_l2(got.mean, ref.mean), logvar=rel_l2(got.logvar, ref.logvar))
+        assert out[f"{B}x{H}x{W}"]["mean"] <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), out
+    return out
+
+
 def check_edge_cases():
     """Empty / minimal / ragged inputs and error behaviour at the boundary."""
     import pytest

@@ -38,9 +38,13 @@ def test_group_norm(C, HW):
     _c().check_group_norm(C, HW, silu=False, seed=1)
 
 
-@pytest.mark.parametrize("prec,L", [("fp32", 256), ("bf16", 256), ("fp16", 1024), ("bf16", 144)])
+@pytest.mark.parametrize("prec,L", [("fp32", 256), ("bf16", 256), ("fp16", 1024), ("bf16", 144), ("bf16", 125), ("fp16", 77)])
 def test_attention(prec, L):
     _c().check_attention(prec, N=2, L=L)
+
+
+def test_token_count_not_multiple_of_8():
+    print(_c().check_odd_token_count("fp16"))
 
 
 def test_resize_bit_exact_vs_pil_golden():
