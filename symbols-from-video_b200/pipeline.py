@@ -45,6 +45,8 @@ class FramePipeline:
         self.device = torch.device(device)
         self._stage = [None, None]
         self._copy_stream = None
+        self._out = {}
+        self.host_batch = int(os.environ.get("SFV_HOST_BATCH", getattr(vae, "chunk", None) or 16))
 
     def _staging(self, i, shape):
         t = self._stage[i]
@@ -63,30 +65,45 @@ class FramePipeline:
         codes, h = self.rbvae.encode_codes(lat.unsqueeze(1), noise_ratio=noise_ratio, U=U)
         return EncodeResult(lat, codes, h.squeeze(1))
 
+    def _pinned(self, name, shape, dtype):
+        t = self._out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._out[name] = t
+        return t
+
     @torch.no_grad()
-    def encode_host(self, frames: torch.Tensor | np.ndarray):
+    def encode_host(self, frames: torch.Tensor | np.ndarray, reuse_output: bool = False):
         """Host uint8 frames [N,H,W,3] (ideally pinned) -> EncodeResult on the HOST.
-        Double-buffered: the H2D copy of batch i+1 overlaps the kernels of batch i."""
+
+        The frames are walked in sub-batches of ``host_batch`` (default: the encoder's chunk): the H2D copy of
+        sub-batch i+1 runs on a copy stream under the kernels of sub-batch i, and each sub-batch's results go down
+        into pinned host buffers asynchronously, so only the first upload and the last download are exposed.
+        ``reuse_output=True`` returns views of the pipeline's pinned buffers (overwritten by the next call)."""
         if isinstance(frames, np.ndarray):
             frames = torch.from_numpy(frames)
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
             raise ValueError(f"expected uint8 [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
-        N = frames.shape[0]
+        N, H, W, _ = frames.shape
+        hb = max(1, min(self.batch, self.host_batch))
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
-        lat_out, code_out, h_out = [], [], []
-        starts = list(range(0, N, self.batch))
+        starts = list(range(0, N, hb))
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        L = self.rbvae.latent_dim if self.rbvae is not None else 0
+        lat_out = self._pinned("lat", (N, 4, H // 8, W // 8), torch.float32)
+        code_out = self._pinned("codes", (N, (L + 31) // 32), torch.int32) if self.rbvae is not None else None
+        h_out = self._pinned("h", (N, L), torch.float32) if self.rbvae is not None else None
 
         def upload(i):
             s = starts[i]
-            chunk = frames[s:s + self.batch]
+            chunk = frames[s:s + hb]
             with torch.cuda.stream(self._copy_stream):
                 if i >= 2:
                     self._copy_stream.wait_event(consumed[i % 2])
-                dst = self._staging(i % 2, chunk.shape)
+                dst = self._staging(i % 2, (hb, H, W, 3))[:chunk.shape[0]]
                 dst.copy_(chunk, non_blocking=True)
                 ready[i % 2].record(self._copy_stream)
             return dst
@@ -99,13 +116,16 @@ class FramePipeline:
                 pending = upload(i + 1)
             r = self.encode_device(cur)
             consumed[i % 2].record(main)
-            lat_out.append(r.latents.to("cpu", non_blocking=True))
+            s0, n = starts[i], cur.shape[0]
+            lat_out[s0:s0 + n].copy_(r.latents, non_blocking=True)
             if r.codes is not None:
-                code_out.append(r.codes.to("cpu", non_blocking=True))
-                h_out.append(r.h.to("cpu", non_blocking=True))
+                code_out[s0:s0 + n].copy_(r.codes, non_blocking=True)
+                h_out[s0:s0 + n].copy_(r.h, non_blocking=True)
         torch.cuda.synchronize(self.device)
-        cat = lambda xs: torch.cat(xs) if xs else None
-        return EncodeResult(cat(lat_out), cat(code_out), cat(h_out))
+        if reuse_output:
+            return EncodeResult(lat_out, code_out, h_out)
+        return EncodeResult(lat_out.clone(), None if code_out is None else code_out.clone(),
+                            None if h_out is None else h_out.clone())
 
 
 def all_gather_ragged(local: torch.Tensor, counts: list[int], group=None):
