@@ -141,6 +141,8 @@ struct IgemmArgs {
 int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
 int launch_conv_in(const void* x, int src_kind, const float* w, const float* bias, float* y, double* stats,
                    int N, int H, int W, cudaStream_t s);
+int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, int y16, int fmt, int N, int H, int W,
+                    float in_scale, cudaStream_t s);
 
 // ---- norm / elementwise ------------------------------------------------------
 // stats: double [N][G][2] accumulators (sum, sumsq) -- zeroed by the caller/kernel.

@@ -91,7 +91,82 @@ conv_in_kernel(const void* __restrict__ x, const float* __restrict__ w, const fl
   }
 }
 
+// Contrastive RBVAE first layer (contrastive_RBVAE_model.py:50-52): conv3x3 3 -> 64, stride 2, pad 1, + ReLU, fed from
+// the reference's fp32 NCHW frames in [0,1].  Same shape of problem as conv_in (K = 27, write-bound: 128 B of 16-bit
+// NHWC per output pixel): a warp owns one output row segment, lane l owns channels 2l, 2l+1 with their 27x2 weights
+// in registers, the (2*TH+1) x (2*TW+1) x 3 input patch is staged in shared memory with coalesced NCHW reads and read
+// back as warp broadcasts, each pixel leaves as one coalesced 128-byte (16-bit) or 256-byte (fp32) row.
+constexpr int RTH = 8, RTW = 32;
+template <bool OUT16>
+__global__ void __launch_bounds__(256)
+rb_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                void* __restrict__ y, int fmt, int H, int W, int Ho, int Wo, float in_scale, int tiles_x, int tiles) {
+  constexpr int PH = 2 * RTH + 1, PW = 2 * RTW + 1;
+  __shared__ float patch[PH][PW][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.y;
+  float wr[27][2];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(w + k * 64 + lane * 2));
+    wr[k][0] = t.x; wr[k][1] = t.y;
+  }
+  const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + lane * 2));
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int y0 = ty * RTH, x0 = tx * RTW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * 3; i += 256) {
+      const int cc = i % PW;
+      const int r = (i / PW) % PH;
+      const int c = i / (PW * PH);
+      const int iy = 2 * y0 - 1 + r, ix = 2 * x0 - 1 + cc;
+      float v = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)n * 3 + c) * H + iy) * W + ix] * in_scale;
+      patch[r][cc][c] = v;
+    }
+    __syncthreads();
+    const int oy = y0 + warp;
+    if (oy < Ho) {
+      const long long row = (((long long)n * Ho + oy) * Wo + x0) * 64 + lane * 2;
+#pragma unroll 2
+      for (int px = 0; px < RTW; ++px) {
+        if (x0 + px >= Wo) break;
+        float a0 = b2.x, a1 = b2.y;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float v = patch[2 * warp + r][2 * px + sx][c];
+              const int k = (r * 3 + sx) * 3 + c;
+              a0 = fmaf(v, wr[k][0], a0); a1 = fmaf(v, wr[k][1], a1);
+            }
+        a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+        if (OUT16) reinterpret_cast<uint32_t*>(y)[(row + (long long)px * 64) >> 1] = pack2_16(a0, a1, fmt);
+        else *reinterpret_cast<float2*>(reinterpret_cast<float*>(y) + row + (long long)px * 64) = make_float2(a0, a1);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+// x fp32 NCHW [N,3,H,W]; w fp32 [27][64] (k = (r*3+s)*3 + c); y NHWC [N,Ho,Wo,64] fp32 (y16 == 0) or 16-bit.
+int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, int y16, int fmt, int N, int H, int W,
+                    float in_scale, cudaStream_t s) {
+  SFV_CHECK(N <= 65535, "rb_conv0: batch too large");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int tiles_x = ceil_div(Wo, RTW), tiles = tiles_x * ceil_div(Ho, RTH);
+  const int per = ceil_div(148 * 4, N);                  // about four blocks per SM over the whole batch
+  const int gx = tiles < per ? tiles : (per < 1 ? 1 : per);
+  ProfScope prof(PROF_IGEMM, 2.0 * N * (double)Ho * Wo * 64 * 27, s);
+  if (y16) rb_conv0_kernel<true><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, fmt, H, W, Ho, Wo, in_scale, tiles_x, tiles);
+  else rb_conv0_kernel<false><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, fmt, H, W, Ho, Wo, in_scale, tiles_x, tiles);
+  SFV_LAUNCH_OK();
+  return 0;
+}
 
 // x: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W]; w: fp32 [27][128]; y: fp32 NHWC [N,H,W,128];
 // stats_or_null: fp64 [N][32][2] (pre-zeroed) receives sum / sum of squares per GroupNorm group.

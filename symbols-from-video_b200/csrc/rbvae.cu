@@ -2,9 +2,9 @@
 // contrastive: 64 / 2).  Reference: models/percep_RBVAE/percep_RBVAE_model.py:46-68,
 // 94-107,172-191; models/contrastive_RBVAE/contrastive_RBVAE_model.py:45-67,93-106,171-190.
 //
-// All arithmetic is fp32 on the CUDA-core implicit GEMM: the binary code is the
-// sign of a small LSTM state, so this part is kept at full precision (0.04 % of
-// the pipeline FLOPs).
+// precision fp32: every layer on CUDA cores in fp32.  bf16 / fp16: the two C -> C stride-2 convs (97 % of the
+// RBVAE FLOPs) run on the tcgen05 kernel with 16-bit operands and fp32 accumulation; conv.0, fc, the LSTM and the
+// threshold stay fp32 -- the binary code is the sign of a small LSTM state.
 #include "common.cuh"
 #include "encoder.h"
 #include <string.h>
@@ -119,14 +119,18 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
     // conv(s2,p1)+ReLU, conv(s2,p1)+ReLU, conv(s2,p1)   (dropout is identity in eval)
     const bool tc = r->prec != SFV_PREC_F32 && r->c1.w16 && r->c2.w16 && h[1] % 2 == 0 && w[1] % 2 == 0 &&
                     h[2] % 2 == 0 && w[2] % 2 == 0;
+    // contrastive first layer (3 -> 64 on full-resolution frames) has its own write-bound kernel
+    const bool c0_direct = r->in_channels == 3 && r->channels == 64;
     if (tc) {
       // 16-bit operands for the two C->C convs (97 % of the RBVAE FLOPs) on the tcgen05 kernel;
       // conv.0 (Cin = 3 or 4) stays on CUDA cores and emits the 16-bit operand directly
-      SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt));
+      if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 1, r->fmt, nn, h[0], w[0], in_scale, s));
+      else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt));
       SFV_TRY(conv_tc(r->c1, r->fmt, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s));
       SFV_TRY(conv_tc(r->c2, r->fmt, a2i, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, nullptr, 0, s));
     } else {
-      SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));
+      if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 0, r->fmt, nn, h[0], w[0], in_scale, s));
+      else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));
       SFV_TRY(conv_f32(r->c1, a1i, SRC_NHWC_F32, nn, h[1], w[1], 2, 1, 1, nullptr, a2i, 1, 1.f, s));
       // third conv output reuses a1 (dead after conv 2)
       SFV_TRY(conv_f32(r->c2, a2i, SRC_NHWC_F32, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, 0, 1.f, s));
