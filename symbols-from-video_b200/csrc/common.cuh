@@ -201,6 +201,9 @@ struct TcGemmArgs {
   // conv_in mode: instead of a 16-bit A tensor, uint8 HWC frames [Nimg][Ho][Wo][3]; the producer warp builds the
   // 3x3x3 patch rows (2u-255, zero padded, duplicated for the hi/lo weight split) straight into the swizzled A tile
   const unsigned char* u8_src;
+  // attention scores: out_16 = softmax over the Cout axis of alpha * (A . B^T), fp32 scores never stored (two passes
+  // over the n-tiles inside one CTA pair; needs out_16 only: no bias / residual / fp32 output / statistics)
+  int softmax_mode;
 };
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s);
 int tc_check_device_error(cudaStream_t s);   // sync + read the watchdog flag

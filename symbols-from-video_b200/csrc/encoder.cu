@@ -474,6 +474,9 @@ struct Fwd {
 
 }  // namespace
 
+// SFV_ATTN_FUSED=0 falls back to materialised fp32 scores + a separate softmax kernel (A/B measurements)
+static const bool g_attn_fused = []() { const char* e = getenv("SFV_ATTN_FUSED"); return !(e && atoi(e) == 0); }();
+
 // Tensor-core attention core for a chunk of images whose score matrices fit S/P:
 //   S = scale * Q K^T (fp32) ; P = softmax(S) (16-bit) ; O = P V + b_v (16-bit)
 // q16/k16: [N][L][*] rows with pitch q_ld/k_ld elements; vT16: [N][C][Lp], S/P: [N][L][Lp], Lp = L rounded up to 8.
@@ -492,10 +495,16 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
     a.b = k16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)k_ld * 2;
     a.b_batch_stride = (unsigned long long)L * k_ld * 2; a.b_batched = 1;
     a.BW = 128; a.BH = 1; a.Wo = L; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
-    a.alpha = scale; a.out_f32 = S; a.ldo = Lp;
-    SFV_TRY(launch_tc_gemm(a, s));
+    a.alpha = scale; a.ldo = Lp;
+    if (g_attn_fused) {            // P = softmax(scale * Q K^T) straight from the GEMM: the fp32 scores stay on chip
+      a.out_16 = P; a.softmax_mode = 1;
+      SFV_TRY(launch_tc_gemm(a, s));
+    } else {
+      a.out_f32 = S;
+      SFV_TRY(launch_tc_gemm(a, s));
+      SFV_TRY(launch_softmax_rows(S, P, 1, fmt, (long long)N * L, L, s, Lp));
+    }
   }
-  SFV_TRY(launch_softmax_rows(S, P, 1, fmt, (long long)N * L, L, s, Lp));
   {
     TcGemmArgs a; memset(&a, 0, sizeof(a));
     a.a = P; a.fmt = fmt; a.a_rank = 3;

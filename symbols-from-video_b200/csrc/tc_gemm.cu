@@ -68,6 +68,11 @@ struct TcParams {
   int num_stages, res_bufs, h16_slots;   // shared-memory plan of this launch
   int res_prefetch;                    // L2-prefetch the residual one tile ahead of its TMA load
   const unsigned char* u8_src;         // conv_in mode (see TcGemmArgs::u8_src)
+  // softmax mode (attention scores): a CTA (pair) owns whole rows -- it walks all n-tiles of its m-tile twice, pass 0
+  // keeps the running row max / sum in registers, pass 1 recomputes the scores and stores P = softmax(alpha * S) in
+  // 16 bit.  The fp32 scores never leave the SM.
+  int softmax_mode, sm_per, n_groups;  // sm_per = 2 * n_tiles_n units per m-tile group
+  FastDiv fd_per;
   int a2_kchunks, a2_k0;               // fused 1x1 branch: extra k-chunks read through the second A map
   unsigned long long* dbg;             // optional per-CTA role cycle counters [grid][8]
   int* err;                            // device watchdog flag
@@ -78,12 +83,20 @@ struct TcParams {
 #define SFV_TC_FINE_DEBUG 0
 #endif
 constexpr bool kFineDbg = SFV_TC_FINE_DEBUG != 0;   // per-phase cycle counters inside the epilogue chunk loop (58 CS2R per tile)
-struct TileCoord { int n_tile, m_tile, tx, ty, img; };
+struct TileCoord { int n_tile, m_tile, tx, ty, img, pass; };
 template <int NCTA>
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int unit, int rank) {
   TileCoord t;
   int um;
-  p.fd_ntn.divmod(unit, um, t.n_tile);
+  if (p.softmax_mode) {
+    int k;
+    p.fd_per.divmod(unit, um, k);          // unit = group * sm_per + pass * n_tiles_n + n_tile
+    t.pass = k >= p.n_tiles_n ? 1 : 0;
+    t.n_tile = k - t.pass * p.n_tiles_n;
+  } else {
+    p.fd_ntn.divmod(unit, um, t.n_tile);
+    t.pass = 0;
+  }
   t.m_tile = um * NCTA + rank;
   int q;
   p.fd_tx.divmod(t.m_tile, q, t.tx);
@@ -207,6 +220,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 }
 __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {       // 2^x, 2 ulp; x <= 0 here
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -477,7 +495,9 @@ struct Cfg {
   static constexpr int kBBytes = (BLOCK_N / NCTA) * kBlockK * 2;      // a CTA pair splits B's rows
   static constexpr int kStageBytes = kABytes + kGroup * kBBytes;
   static constexpr int kTxBytes = kATxBytes + kGroup * kBBytes;
-  static constexpr int kSets = BLOCK_N == 128 ? 2 : 1;               // epilogue warps per TMEM lane quarter
+  // epilogue warps per TMEM lane quarter: two (each half of the columns) for BLOCK_N = 128 and for the non-HALO
+  // BLOCK_N = 256 kernels (attention GEMMs, 64x64 convs: short K, epilogue-bound with four warps)
+  static constexpr int kSets = (BLOCK_N == 128 || (BLOCK_N == 256 && !HALO)) ? 2 : 1;
   static constexpr int kEpiWarps = 4 * kSets;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   // The staging rings are sized per launch (a conv that writes only 16-bit outputs needs no fp32 ring), and
@@ -509,6 +529,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // 256-pixel x BLOCK_N tile; rank 0 issues the MMAs for both (tcgen05 cta_group::2).
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int unit0 = blockIdx.x / NCTA, unit_step = gridDim.x / NCTA;
+  // it-th work unit of this CTA (pair), or -1: round-robin tiles, or -- softmax mode -- whole m-tile groups
+  auto unit_of = [&](int it) -> int {
+    if (!p.softmax_mode) { const int u = unit0 + it * unit_step; return u < p.n_units ? u : -1; }
+    int g, k;
+    p.fd_per.divmod(it, g, k);
+    const int grp = unit0 + g * unit_step;
+    return grp < p.n_groups ? grp * p.sm_per + k : -1;
+  };
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -614,7 +642,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ok = false;                                          // skip the TMA producer loop below
         }
       }
-      for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+      for (int it = 0; ok; ++it) {
+        const int unit = unit_of(it);
+        if (unit < 0) break;
         const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);   // m_tile may be a phantom tile (>= n_tiles_m): all OOB -> zeros
         const int n_tile = tc.n_tile, m_tile = tc.m_tile, tx = tc.tx, ty = tc.ty, img = tc.img;
         int base[5] = {0, 0, 0, 0, 0};
@@ -691,7 +721,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
       unsigned long long t_full = 0, t_tempty = 0, t_start = clock64();
-      for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+      for (int it = 0; ok; ++it) {
+        if (unit_of(it) < 0) break;
         const unsigned long long tw0 = p.dbg ? clock64() : 0;
         ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, abort_flag, p.err, 2);
         if (p.dbg) t_tempty += clock64() - tw0;
@@ -772,7 +803,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     // kSets == 2 (Cout = 128, 4 channels per group): per-lane register partials for this warp's 16 groups,
     // reduced across the 32 rows once per image (one 32-value recursive-halving pass, 31 shuffles)
-    constexpr bool kRegStats = C::kSets == 2;
+    constexpr bool kRegStats = C::kSets == 2 && BLOCK_N == 128;
     float gacc[kRegStats ? 32 : 1];
 #pragma unroll
     for (int i = 0; i < (kRegStats ? 32 : 1); ++i) gacc[i] = 0.f;
@@ -841,7 +872,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (use_tma && has_res) {
       for (int g = 0; g < (kResBufs > 1 ? kResBufs - 1 : 1); ++g) issue_residual(g, g);
     }
-    for (int unit = unit0; unit < p.n_units && ok; unit += unit_step) {
+    float sm_m = -INFINITY, sm_l = 0.f, sm_inv = 0.f;      // softmax mode: this lane's row max (log2 domain), sum, max + log2(sum)
+    for (int it = 0; ok; ++it) {
+      const int unit = unit_of(it);
+      if (unit < 0) break;
       const unsigned long long t_top = p.dbg ? clock64() : 0;
       const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);
       const int n_tile = tc.n_tile, m_tile = tc.m_tile, tx = tc.tx, ty = tc.ty, img = tc.img;
@@ -868,6 +902,87 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           //      swizzled staging tiles, so shared-memory accesses are conflict-free.
           const int sw = lane & 7;                 // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
           const int sw16 = (lane >> 1) & 3;        // 64B swizzle:  chunk j of row r lives at j ^ ((r >> 1) & 3)
+          if (p.softmax_mode) {
+            // ---- attention scores: t = alpha * log2(e) * s.  Pass 0: online row max / sum (one row per lane, no
+            //      cross-lane traffic); pass 1: P = 2^(t - max - log2(sum)), stored in 16 bit by TMA.  Columns past the
+            //      last key are masked.  The TMEM load of chunk c+1 is in flight while chunk c is processed, and the
+            //      max / sum reductions run as four independent chains (a single warp per scheduler hides no latency).
+            const float a2 = p.alpha * 1.4426950408889634f;
+            if (tc.pass == 0 && n_tile == 0) { sm_m = -INFINITY; sm_l = 0.f; }
+            if (tc.pass == 1 && n_tile == 0) {
+              if constexpr (C::kSets == 2) {
+                // two warps share a row (column halves): merge their (max, sum) through shared memory; the pair of
+                // warps of one TMEM lane quarter meets on its own named barrier (both walk the same unit sequence)
+                float* ex = gn_acc;                               // [epilogue warp][lane][2], GroupNorm is off in this mode
+                ex[(ew * 32 + lane) * 2] = sm_m; ex[(ew * 32 + lane) * 2 + 1] = sm_l;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                const int other = (eset ^ 1) * 4 + quarter;
+                const float m1 = ex[(other * 32 + lane) * 2], l1 = ex[(other * 32 + lane) * 2 + 1];
+                const float m = fmaxf(sm_m, m1);
+                sm_l = sm_l * ex2_approx(sm_m - m) + l1 * ex2_approx(m1 - m);
+                sm_m = m;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // scratch may be rewritten after this
+              }
+              sm_inv = sm_m + log2f(sm_l);
+            }
+            auto chunk = [&](const uint32_t (&v)[32], int c) {
+              const int col0 = n_tile * BLOCK_N + cbase + c * 32;
+              if (!(tile_ok && col0 < p.Cout)) return;
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              if (p.Cout - col0 < 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = (j < p.Cout - col0) ? f[j] : -INFINITY;
+              }
+              if (tc.pass == 0) {
+                float m4[4] = {f[0], f[1], f[2], f[3]};
+#pragma unroll
+                for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], f[j]);
+                const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                const float m_new = fmaxf(sm_m, mx * a2);       // alpha > 0
+                float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) l4[j & 3] += ex2_approx(fmaf(f[j], a2, -m_new));
+                sm_l = sm_l * ex2_approx(sm_m - m_new) + ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+                sm_m = m_new;
+              } else {
+                const int hslot = p.h16_slots == 2 ? (g_cur & 1) : 0;
+                const uint32_t hb = h16_s + hslot * 2048 + lane * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t w4[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    w4[q] = pack2_16(ex2_approx(fmaf(f[8 * j + 2 * q], a2, -sm_inv)),
+                                     ex2_approx(fmaf(f[8 * j + 2 * q + 1], a2, -sm_inv)), p.fmt);
+                  sts128u(hb + ((j ^ sw16) << 4), w4[0], w4[1], w4[2], w4[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (elect_one_sync()) {
+                  tma_store_4d(&tmO16, h16_s + hslot * 2048, col0, tx * p.BW + wx, ty * p.BH + wy, img);
+                  tma_store_commit();
+                  if (deep_rings) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
+                __syncwarp();
+              }
+              ++g_cur;
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row + cbase, va);
+#pragma unroll 1
+            for (int c = 0; c < kNChunk; c += 2) {
+              tmem_ld_wait();
+              if (c + 1 < kNChunk) tmem_ld32(t_row + cbase + (c + 1) * 32, vb);
+              chunk(va, c);
+              if (c + 1 < kNChunk) {
+                tmem_ld_wait();
+                if (c + 2 < kNChunk) tmem_ld32(t_row + cbase + (c + 2) * 32, va);
+                chunk(vb, c + 1);
+              }
+            }
+          } else
 #pragma unroll (kRegStats ? 2 : 1)
           for (int c = 0; c < kNChunk; ++c, ++g_cur, rslot = (rslot + 1 == kResBufs) ? 0 : rslot + 1, rphase ^= (rslot == 0)) {
             const int c0 = c * 32;                              // column inside this warp's share
@@ -1140,19 +1255,27 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   // residual load sits in the chain) single-slot rings buy the third stage instead (measured: 448 -> 379 us on the
   // 512->512 conv2 at 128x128, but 513 -> 551 us on the 256->256 one, hence the threshold).
   p.h16_slots = need_h16 ? 2 : 0;
-  p.res_bufs = !need_f32 ? 0 : ((C::kSets == 2 && need_h16) ? 2 : 3);
+  // eight epilogue warps hold half as many chunks each: two-slot rings suffice when staging is scarce
+  p.res_bufs = !need_f32 ? 0 : ((C::kSets == 2 && (need_h16 || BLOCK_N == 256)) ? 2 : 3);
   {
-    const int want = HALO ? 3 : 4;
+    const int want = HALO ? 3 : 6;      // non-HALO stages hold one k-chunk (24-32 KB): six of them cover the load latency
     const long long k_chunks_total = (long long)p.ntaps * p.kchunks + p.a2_kchunks;
     constexpr int chunks_per_warp = BLOCK_N >= 32 ? BLOCK_N / C::kSets / 32 : 1;
     const long long chunk_budget = k_chunks_total * (BLOCK_N * kBlockM * kBlockK / 4096) / chunks_per_warp;
-    if (C::stages_for(p.res_bufs, p.h16_slots) < want && chunk_budget >= (p.residual ? 4000 : 2000) && g_epi_slots_auto) {
+    const int floor_stages = HALO ? 2 : 3;
+    const bool have_slack = chunk_budget >= (p.residual ? 4000 : 2000);
+    if (g_epi_slots_auto && (C::stages_for(p.res_bufs, p.h16_slots) < floor_stages ||
+                             (C::stages_for(p.res_bufs, p.h16_slots) < want && have_slack))) {
+      const int need = C::stages_for(p.res_bufs, p.h16_slots) < floor_stages && !have_slack ? floor_stages : want;
       const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+      int best_r = p.res_bufs, best_h = p.h16_slots;
       for (int i = 0; i < 4; ++i) {
         const int r = need_f32 ? cand[i][0] : 0, h = need_h16 ? cand[i][1] : 0;
         if (r > p.res_bufs || h > p.h16_slots) continue;
-        if (C::stages_for(r, h) >= want) { p.res_bufs = r; p.h16_slots = h; break; }
+        best_r = r; best_h = h;                                  // candidates get shallower: the last one has the most stages
+        if (C::stages_for(r, h) >= need) break;
       }
+      p.res_bufs = best_r; p.h16_slots = best_h;
     }
     if (g_epi_slots_r >= 0 && need_f32) p.res_bufs = g_epi_slots_r;       // SFV_EPI_SLOTS=r,h experiment override
     if (g_epi_slots_h >= 0 && need_h16) p.h16_slots = g_epi_slots_h;
@@ -1161,7 +1284,8 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
   const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots);
   const int max_units = g_num_sms / NCTA;
-  const int grid = (p.n_units < max_units ? p.n_units : max_units) * NCTA;
+  const int n_sched = p.softmax_mode ? p.n_groups : p.n_units;      // schedulable items: tiles, or whole m-tile groups
+  const int grid = (n_sched < max_units ? n_sched : max_units) * NCTA;
   // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
   const double flops = 2.0 * (double)p.Wo * p.Ho * p.n_img * p.Cout * (double)p.ntaps * p.kchunks * kBlockK;
   // conv_in (K = 27, write-bound) is accounted with the other first-layer kernels, not with the tensor-bound GEMMs
@@ -1255,6 +1379,13 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.n_tiles = p.n_tiles_m * p.n_tiles_n;
   p.n_units = ceil_div(p.n_tiles_m, ncta) * p.n_tiles_n;
   p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+  p.softmax_mode = a.softmax_mode;
+  p.sm_per = 2 * p.n_tiles_n; p.n_groups = ceil_div(p.n_tiles_m, ncta); p.fd_per = make_fastdiv(p.sm_per);
+  if (a.softmax_mode) {
+    SFV_CHECK(a.out_16 && !a.out_f32 && !a.residual && !a.bias && !a.gn_stats && !a.relu && !a.a2 && !a.u8_src && a.block_n >= 32,
+              "tc_gemm: softmax mode takes a 16-bit output only");
+    p.n_units = p.n_groups * p.sm_per;
+  }
   p.epi_mode = g_epi_mode;
   p.res_prefetch = g_res_prefetch;
   p.dbg = g_dbg;
@@ -1276,6 +1407,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
                        (!a.residual || ((uintptr_t)a.residual & 15) == 0);
   p.epi_mode = tma_epi ? 1 : 0;
   SFV_CHECK(tma_epi || a.Cout % 4 == 0, "tc_gemm: Cout %% 4 != 0 needs the TMA epilogue (ldo %% 8 == 0, aligned outputs)");
+  SFV_CHECK(tma_epi || !a.softmax_mode, "tc_gemm: softmax mode needs the TMA epilogue");
   if (tma_epi) {
     const cuuint32_t bx = a.BW < 32 ? a.BW : 32, by = 32 / bx;
     cuuint64_t dims[4] = {(cuuint64_t)a.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.Nimg};
