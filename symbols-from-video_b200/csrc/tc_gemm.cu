@@ -17,8 +17,19 @@
 //   ReLU, then write fp32 and/or 16-bit NHWC rows (and optional GroupNorm
 //   partial sums for the consumer's normalisation).
 //
+// * Variants selected per launch:
+//     HALO      3x3 stride-1 row tiles: one 130-pixel A box serves the three horizontal taps of a filter row
+//     NCTA = 2  CTA pairs (tcgen05 cta_group::2) share a 256-pixel tile and split the B tile
+//     a2        a second A tensor map appends a fused 1x1 branch (nin_shortcut) as extra K chunks
+//     u8_src    conv_in: the producer warp builds the A tile from uint8 frames (exact 2u-255 operand)
+//     softmax   attention scores: two passes over the key tiles, P = softmax(alpha S) stored in 16 bit
+//   Epilogue outputs leave through swizzled staging tiles and TMA bulk stores; residual tiles arrive by TMA.
+//
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
 // allocator, warps 2.. = epilogue (4 or 8 warps; TMEM lane quarter = warp_idx % 4).
+//
+// Environment knobs (experiments / A-B measurements, defaults are the tuned choices): SFV_NCTA, SFV_EPI, SFV_HALO,
+// SFV_EPI_SLOTS, SFV_RES_PREFETCH, SFV_TC_DEBUG (role-cycle accounting, tools/tc_debug.py).
 #include "common.cuh"
 #include <cuda.h>
 
