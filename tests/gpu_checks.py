@@ -586,6 +586,28 @@ def check_odd_token_count(prec="fp16"):
     return out
 
 
+def check_shape_sweep(prec="fp16"):
+    """Seeded sweep over frame shapes that stress tile clipping, HALO row tiles, CTA-pair selection and the ragged
+    chunk tail: widths / heights around the 128-pixel tile and the pair boundary, tiny frames, odd batch sizes."""
+    out = {}
+    vae, sd = make_vae(prec, 0)
+    shapes = [(1, 8, 16), (3, 16, 8), (2, 24, 136), (1, 136, 24), (1, 72, 264), (2, 128, 128), (1, 120, 248),
+              (5, 32, 40), (1, 264, 72), (1, 8, 1032), (17, 16, 16)]
+    worst = 0.0
+    for i, (B, H, W) in enumerate(shapes):
+        u8 = frames.synthetic_frames(B, H, W, 100 + i, smooth=(i % 2 == 0) and min(H, W) >= 16)
+        got = vae.encode_uint8(torch.from_numpy(u8).to(DEV))
+        vae.check_async_error()
+        ref = kl_f8.encode(frames.normalise_u8(u8), sd)
+        e = rel_l2(got.parameters, ref.parameters)
+        out[f"{B}x{H}x{W}"] = e
+        worst = max(worst, e)
+        assert torch.isfinite(got.parameters).all(), (B, H, W)
+        assert e <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), (B, H, W, e)
+    out["worst"] = worst
+    return out
+
+
 def check_edge_cases():
     """Empty / minimal / ragged inputs and error behaviour at the boundary."""
     import pytest

@@ -43,6 +43,11 @@ def test_attention(prec, L):
     _c().check_attention(prec, N=2, L=L)
 
 
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_shape_sweep(prec):
+    print(_c().check_shape_sweep(prec))
+
+
 def test_token_count_not_multiple_of_8():
     print(_c().check_odd_token_count("fp16"))
 

@@ -29,7 +29,8 @@ def plan():
               ("attn/fp32", "check_attention('fp32',2,256)"), ("attn/bf16", "check_attention('bf16',2,256)"),
               ("attn/fp16", "check_attention('fp16',2,1024)"), ("attn/bf16/L144", "check_attention('bf16',2,144)"),
               ("attn/bf16/L125", "check_attention('bf16',3,125)"), ("attn/fp16/L77", "check_attention('fp16',1,77)"),
-              ("enc/odd_tokens", "check_odd_token_count()"),
+              ("enc/odd_tokens", "check_odd_token_count()"), ("shapes/fp16", "check_shape_sweep('fp16')"),
+              ("shapes/fp32", "check_shape_sweep('fp32')"), ("shapes/bf16", "check_shape_sweep('bf16')"),
               ("resize", "check_resize()"), ("hamming", "check_hamming()")]
     for prec in ("fp32", "bf16", "fp16"):
         items.append((f"taps/{prec}", f"check_encoder_taps({prec!r})"))
