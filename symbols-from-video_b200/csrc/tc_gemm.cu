@@ -1338,8 +1338,14 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
                   ((uintptr_t)a.u8_src & 3) == 0 && a.Cout == 128,
               "tc_gemm: conv_in mode needs 128-pixel row tiles, one k-chunk, Cout 128 and a 4-byte aligned frame");
   // HALO variant: 3x3 stride-1 conv, 128-pixel row-segment tiles, taps ordered row-major with dx = -1,0,+1
+  // BLOCK_N = 256: a HALO stage is 65 KB and its kernel has four epilogue warps, so (measured, 8 frames of 512^2)
+  //   Cin = 128 (two k-chunks per tap, epilogue-bound)               239 us HALO vs 215 us plain with eight epilogue warps
+  //   Cin = 256 with residual + fp32 + 16-bit outputs (two stages)   489 us HALO vs 475 us plain
+  // go to the plain kernel; every other 256-wide 3x3 layer is faster with HALO (417 vs 434, 375 vs 396, 385 vs 417 us).
+  const bool halo256 = a.block_n == 256 && g_halo >= 2 && a.kchunks >= 4 &&
+                       !(a.kchunks < 8 && a.residual && a.out_f32 && a.out_16);
   const bool halo = !a.u8_src && g_halo && g_ncta_max >= 2 && !a.b_batched && a.halo_ok && a.ntaps == 9 && a.BW == 128 && a.BH == 1 &&
-                    (a.block_n == 128 || (a.block_n == 256 && g_halo >= 2)) && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
+                    (a.block_n == 128 || halo256) && a.dim_x == 1 && (long long)ceil_div(a.Wo, 128) * a.Ho * a.Nimg >= 2;
   if (!a.u8_src) {
     cuuint64_t dims[5], strides[5]; cuuint32_t box[5];
     for (int i = 0; i < 5; ++i) {
