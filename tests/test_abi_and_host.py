@@ -240,3 +240,19 @@ def test_resident_pair_dataset_matches_reference_golden(mode):
     assert np.array_equal(ds._load_embedding(5).numpy(), _toy_embeddings()["0000000005.jpg"][0])
     with pytest.raises(ValueError):
         sfv_b200.ShuffledStatePairDataset(_toy_embeddings(), segs, mode="bogus", device="cpu")
+
+
+def test_evaluation_host_logic():
+    """assign_label / labels_from_flags (embedding_matching.py:195-206) and the occlusion geometry (:180)."""
+    flags = [74, 206, 282, 389]                                   # transition_flags.txt: chinese_chess
+    idx = [0, 73, 74, 75, 205, 206, 281, 282, 388, 389, 479]
+    want = [0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 4]
+    assert [sfv_b200.assign_label(i, flags) for i in idx] == want
+    assert sfv_b200.labels_from_flags(idx, flags).tolist() == want
+    assert sfv_b200.labels_from_flags([], flags).tolist() == []
+    assert sfv_b200.evaluation.occlusion_size(432, 768, 0.2) == int(np.sqrt(0.2 * 432 * 768))
+    # CPU tensors are refused by the device entry points (no CPU fallback)
+    with pytest.raises(Exception):
+        sfv_b200.state_consistency(torch.zeros(4, 1, dtype=torch.int32), torch.zeros(4, dtype=torch.int32), 2)
+    with pytest.raises(Exception):
+        sfv_b200.perturb_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
