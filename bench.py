@@ -155,6 +155,9 @@ def run_reference(args, rank, world):
     CPU kernels), fp32, all host threads, each step a bounded sample of the workload."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count())
     import torch
     import sfv_b200                     # weights / frames generators only; nothing of ours is on the timed path
     sd = sfv_b200.init_encoder_state_dict(0)
