@@ -256,3 +256,15 @@ def test_evaluation_host_logic():
         sfv_b200.state_consistency(torch.zeros(4, 1, dtype=torch.int32), torch.zeros(4, dtype=torch.int32), 2)
     with pytest.raises(Exception):
         sfv_b200.perturb_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every prototype in include/sfv.h has as many parameters as its ctypes argtypes entry (ABI drift guard)."""
+    hdr = open(os.path.join(ROOT, "include", "sfv.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)                 # drop comments
+    protos = dict(re.findall(r"\b(sfv_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(sfv_b200._lib.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([q for q in params.split(",") if q.strip()])
+        assert n == len(sfv_b200._lib.SIGNATURES[name][1]), (name, n, len(sfv_b200._lib.SIGNATURES[name][1]))
