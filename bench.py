@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- frames/sec 512x512 -> binary code (BASELINE.json metric, configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c4|c5]
 
 A "step" is one pass of the hot path over one batch of synthetic frames:
 uint8 [64,512,512,3] -> KL-f8 encoder -> posterior mode * 0.18215 -> percep RBVAE
@@ -11,10 +11,15 @@ encoder -> bit-packed code (latent_dim 25, noise_ratio 0).
           H2D of the frames and D2H of latents + codes inside the timed region
   roofline     : tcgen05 implicit-GEMM kernel, algorithmic FLOPs / its summed
                  CUDA-event launch durations, against MEASURED_PEAKS.json
-  cpu_baseline : the oracle port of the reference's CPU path on a bounded sample
+  cpu_baseline : the UNMODIFIED reference modules (oracle/_ref, placed there by
+                 oracle/build_ref.py) on the host cores, on a bounded sample; the
+                 oracle port is checked against them in the same run
 N > 1 (torchrun, one rank per GPU): each rank encodes its own contiguous range of
-64 frames (weak scaling, no data-path collective) and the packed codes + latents
-are all-gathered with NCCL inside the step; time = max over ranks.
+64 frames (weak scaling, no data-path collective); its kernels write latents, codes
+and h straight into its block of double-buffered gather buffers, and one in-place
+NCCL all-gather per tensor runs asynchronously under the next step; time = max over
+ranks.  Other BASELINE configs: --config c5 (1024x1024, batch 16), --config c4
+(contrastive RBVAE on 512x512 frame pairs, batch 256).
 """
 from __future__ import annotations
 
@@ -33,6 +38,14 @@ if ROOT not in sys.path:
 
 R, BATCH, LATENT_DIM = 512, 64, 25
 N_INPUT_BUFFERS = 4          # 4 x 50 MB of distinct frames > 126 MB L2: inputs never L2-resident across steps
+RB_GAINS = dict(fc_gain=100.0, bias_gain=0.002, ih_gain=8.0)   # codes follow the frame (weights.make_rbvae_responsive)
+PARITY_FRAMES = 16
+DTYPE_NAMES = {"mixed": "mixed fp16/bf16 operands, fp32 accumulate", "bf16": "bf16", "fp16": "fp16", "fp32": "f32"}
+OPERAND_FORMATS = {
+    "mixed": "fp16: weights (per-layer 2^k scale), GroupNorm+SiLU outputs, conv1 outputs, x copies (x 2^-6); "
+             "bf16: q, k, V^T, P, attention output; fp32: accumulators, residual stream, GroupNorm statistics",
+    "bf16": "bf16 operands, fp32 accumulate / residual stream", "fp16": "fp16 operands, fp32 accumulate / residual stream",
+    "fp32": "fp32 CUDA-core check mode"}
 
 
 def peaks():
@@ -114,75 +127,220 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def build_models(precision):
-    import torch
+def make_weights(res):
+    """Seeded random-init weights with the reference key names (no checkpoint exists offline).  The RBVAE's fc /
+    LSTM-input weights are boosted and its biases damped so the binary code depends on the frame: on the default
+    init every frame gets the same code and a code comparison would prove nothing."""
     import sfv_b200
-    sd = sfv_b200.init_encoder_state_dict(0)       # seeded random init with the reference key names
-    rsd = sfv_b200.init_rbvae_state_dict(4, LATENT_DIM, (R // 64, R // 64), seed=1)
+    sd = sfv_b200.init_encoder_state_dict(0)
+    rsd = sfv_b200.make_rbvae_responsive(sfv_b200.init_rbvae_state_dict(4, LATENT_DIM, (res // 64, res // 64), seed=1),
+                                         **RB_GAINS)
+    return sd, rsd
+
+
+def build_models(precision, res=R):
+    import sfv_b200
+    sd, rsd = make_weights(res)
     vae = sfv_b200.AutoencoderKL(precision=precision)
     vae.load_state_dict(sd)
-    # the two 256->256 RBVAE convs follow the encoder's operand format (conv.0, fc, LSTM stay fp32)
-    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, LATENT_DIM, LATENT_DIM, input_hw=(R // 8, R // 8),
+    # the two 256->256 RBVAE convs follow the encoder's operand mode (conv.0, fc, LSTM stay fp32)
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, LATENT_DIM, LATENT_DIM, input_hw=(res // 8, res // 8),
                                    precision=os.environ.get("SFV_RBVAE_PRECISION", precision))
     rb.load_state_dict(rsd)
     return vae, rb, sd, rsd
 
 
-def workload_name(batch):
-    """The one workload both arms are quoted on (BASELINE.json configs[1])."""
-    return (f"BASELINE configs[1]: percep pipeline {R}x{R} uint8 frames -> KL-f8 encoder -> "
-            f"4x{R // 8}x{R // 8} latent -> RBVAE binary code (latent_dim {LATENT_DIM}), batch {batch} per GPU")
+def workload_name(batch, res=R):
+    """The one workload both arms are quoted on (BASELINE.json configs[1]; configs[4] at 1024)."""
+    cfg = {512: "configs[1]", 1024: "configs[4]", 256: "configs[0]"}.get(res, "custom")
+    return (f"BASELINE {cfg}: percep pipeline {res}x{res} uint8 frames -> KL-f8 encoder -> "
+            f"4x{res // 8}x{res // 8} latent -> RBVAE binary code (latent_dim {LATENT_DIM}), batch {batch} per GPU")
 
 
-def cpu_port_fps(sd, rsd, n_frames, frames_u8):
-    """Oracle port of the reference CPU path (fp32, all host threads) on n_frames frames."""
+# ---- the CPU side: the unmodified reference (oracle/_ref) and the oracle port ----------------------------------
+def reference_models(sd, rsd, res):
+    """The reference's own AutoencoderKL and percep Seq2SeqBinaryVAE (unmodified files, oracle/build_ref.py), with
+    fc resized for the latent of a res x res frame (the reference hard-wires 88x160).  None if absent."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None
+    return ref_shim.autoencoder_kl(sd), ref_shim.rbvae("percep", 4, LATENT_DIM, rsd, feat_hw=(res // 64, res // 64))
+
+
+def cpu_reference(models, frames_u8):
+    """frames -> latents -> hard codes through the reference's public API, exactly the calls of
+    get_percep_embeddings.py:94-101 (mode() instead of sample()) and percep_RBVAE_model.py:172-191."""
     import torch
+    from oracle import frames
+    vae, rb = models
+    x = frames.normalise_u8(frames_u8)            # load_img: /255, HWC->NCHW, 2x-1 (get_percep_embeddings.py:67-71)
+    t0 = time.time()
+    with torch.no_grad():
+        post = vae.encode(x)
+        lat = 0.18215 * post.mode()
+        z = rb.encode(lat[:, None], temperature=0.5, hard=True, noise_ratio=0.0)
+    dt = time.time() - t0
+    return len(frames_u8) / dt, dt, dict(z=z[:, 0].numpy(), lat=lat)
+
+
+def cpu_port(sd, rsd, frames_u8):
+    """The oracle port of the same path (also yields h, the thresholded LSTM state, for the |h| < 1e-3 band)."""
     from oracle import frames, kl_f8, rbvae as orb
-    torch.set_num_threads(os.cpu_count())
-    x = frames.normalise_u8(frames_u8[:n_frames])
+    x = frames.normalise_u8(frames_u8)
     t0 = time.time()
     post = kl_f8.encode(x, sd)
     lat = kl_f8.first_stage_encoding(post, use_mode=True)
     z, h = orb.encode(lat[:, None], rsd, hard=True, noise_ratio=0.0, return_h=True)
     dt = time.time() - t0
-    return n_frames / dt, dt, dict(z=z[:, 0].numpy(), h=h[:, 0].numpy(), lat=lat)
+    return len(frames_u8) / dt, dt, dict(z=z[:, 0].numpy(), h=h[:, 0].numpy(), lat=lat)
+
+
+def port_vs_reference(ref, port):
+    import numpy as np
+    return dict(latent_maxabs=float((ref["lat"] - port["lat"]).abs().max()),
+                latent_rel_l2=float((ref["lat"] - port["lat"]).norm() / ref["lat"].norm()),
+                code_bits_differing=int((ref["z"] != port["z"]).sum()), bits=int(np.asarray(ref["z"]).size))
+
+
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core."""
+    import torch
+    n = os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["MKL_NUM_THREADS"] = str(n)
+    torch.set_num_threads(n)
+    return n
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference
-    is Python on PyTorch and cannot travel to the GPU box, so the timed code is the oracle
-    port (oracle/kl_f8.py, oracle/rbvae.py: the reference's call sequence on the same ATen
-    CPU kernels), fp32, all host threads, each step a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path -- its unmodified modules from
+    oracle/_ref (oracle port only if they are absent), fp32, all host threads, each step a bounded sample
+    (8 frames) of the workload, same frames and weights as the GPU arm's first batch."""
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     os.environ["MKL_NUM_THREADS"] = str(os.cpu_count())
     import torch
     import sfv_b200                     # weights / frames generators only; nothing of ours is on the timed path
-    sd = sfv_b200.init_encoder_state_dict(0)
-    rsd = sfv_b200.init_rbvae_state_dict(4, LATENT_DIM, (R // 64, R // 64), seed=1)
-    sample = 2
-    u8 = sfv_b200.synthetic_frames(sample, R, R, 1234, smooth=True).numpy()
+    cores = host_threads()
+    res = args.res
+    sd, rsd = make_weights(res)
+    sample = 8 if res <= 512 else 2
+    u8 = sfv_b200.synthetic_frames(args.batch, res, res, 1234, smooth=True).numpy()[:sample]
+    models = reference_models(sd, rsd, res)
+    kind = "reference" if models is not None else "port"
+    run = (lambda f: cpu_reference(models, f)) if models is not None else (lambda f: cpu_port(sd, rsd, f))
     for _ in range(min(args.warmup, 1)):
-        cpu_port_fps(sd, rsd, 1, u8)
-    times = []
+        run(u8[:1])
+    times, last = [], None
     for _ in range(args.steps):
-        fps, dt, _ = cpu_port_fps(sd, rsd, sample, u8)
+        fps, dt, last = run(u8)
         times.append(dt)
     tot = sum(times)
     val = sample * len(times) / tot
-    line = dict(impl="reference", metric="frames_per_sec_512x512_to_binary_code", value=val, unit="frames/s",
+    agree = None
+    if models is not None:
+        _, _, port = cpu_port(sd, rsd, u8)
+        agree = port_vs_reference(last, port)
+    # BASELINE configs[0] exactly as BASELINE.md section 4 defines the CPU baseline: 8 frames of 256x256, fp32,
+    # 1 warm-up + best of 3
+    c0 = None
+    if res == 512 and not args.no_config0:
+        sd0, rsd0 = make_weights(256)
+        m0 = reference_models(sd0, rsd0, 256)
+        u0 = sfv_b200.synthetic_frames(8, 256, 256, 1234, smooth=True).numpy()
+        run0 = (lambda f: cpu_reference(m0, f)) if m0 is not None else (lambda f: cpu_port(sd0, rsd0, f))
+        run0(u0)
+        best = min(run0(u0)[1] for _ in range(3))
+        c0 = dict(workload=workload_name(8, 256), value=8 / best, unit="frames/s", seconds_per_batch=best,
+                  timing="1 warm-up + best of 3, wall clock", kind=kind, cores=cores)
+    line = dict(impl="reference", metric=f"frames_per_sec_{res}x{res}_to_binary_code", value=val, unit="frames/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * tot / len(times),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=workload_name(args.batch), frames_per_step_per_gpu=args.batch,
-                            weights="seeded random init (no checkpoint offline)",
+                config=dict(workload=workload_name(args.batch, res), frames_per_step_per_gpu=args.batch,
+                            weights="seeded random init (no checkpoint offline), RBVAE fc / LSTM-input gains so codes follow the frame",
                             sample_frames_per_step=sample, operand_format="f32",
-                            note="CPU arm: each step is a bounded sample of the batch (same frames, same weights)"),
-                cpu_baseline=dict(value=val, unit="frames/s", cores=os.cpu_count(), kind="port",
-                                  sample=f"{sample} frames of {R}x{R} per step, fp32, torch CPU"),
+                            note="CPU arm: each step is a bounded sample of the batch (the first frames of the GPU arm's "
+                                 "first batch, same weights)"),
+                cpu_baseline=dict(value=val, unit="frames/s", cores=cores, kind=kind,
+                                  sample=f"{sample} frames of {res}x{res} per step, fp32, "
+                                         + ("unmodified reference modules (oracle/_ref)" if kind == "reference"
+                                            else "oracle port (oracle/_ref absent)")),
+                port_vs_reference=agree, baseline_config0=c0,
                 e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
+
+
+# ---- BASELINE configs[3]: contrastive RBVAE on 512x512 frame pairs ----------------------------------------------
+def run_contrastive(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import sfv_b200
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    L, Rc, pairs = 32, 512, args.batch
+    rsd = sfv_b200.init_rbvae_state_dict(3, L, (Rc // 8, Rc // 8), channels=64, num_layers=2, seed=8)
+    rb = sfv_b200.Seq2SeqBinaryVAE(3, 3, L, L, kind="contrastive", input_hw=(Rc, Rc), precision=args.precision)
+    rb.load_state_dict(rsd)
+    g = torch.Generator().manual_seed(99 + rank)
+    n_buf = 2
+    # frames in [0,1] fp32 NCHW (what the reference's dataset yields), pairs = T = 2; sub-batches of 64 pairs
+    sub = 64
+    bufs = [[torch.rand(sub, 2, 3, Rc, Rc, generator=g).to(dev) for _ in range(max(1, pairs // sub))] for _ in range(n_buf)]
+    lib = sfv_b200.lib()
+
+    def step(i):
+        out = None
+        for x in bufs[i % n_buf]:
+            out = rb.encode_codes(x)
+        return out
+
+    for i in range(args.warmup):
+        step(i)
+    rb.check_async_error(dev)
+    launches0 = lib.sfv_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    rb.check_async_error(dev)
+    if rank == 0:
+        n_pairs = (pairs // sub if pairs >= sub else 1) * sub
+        frames_total = 2 * n_pairs * world * args.steps
+        fps = frames_total / (ms / 1e3)
+        # algorithmic HBM bytes per frame: fp32 NCHW frame in, 16-bit conv0/conv1 maps out+in, conv2 fp32 out + fc in
+        ch = 64
+        px = [(Rc // 2) ** 2, (Rc // 4) ** 2, (Rc // 8) ** 2]
+        bpf = 3 * Rc * Rc * 4 + 2 * px[0] * ch * 2 + 2 * px[1] * ch * 2 + 2 * px[2] * ch * 4
+        pk = peaks()
+        print(json.dumps(dict(
+            metric="frames_per_sec_contrastive_512x512_to_binary_code", value=fps, unit="frames/s", n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+            vs_baseline=None, dtype=DTYPE_NAMES.get(args.precision, args.precision), data="synthetic",
+            config=dict(workload=f"BASELINE configs[3]: contrastive_RBVAE encoder on 512x512 frame pairs, {n_pairs} pairs per GPU per step",
+                        l2_policy=f"{n_buf} rotating input sets of {n_pairs * 2 * 3 * Rc * Rc * 4 >> 20} MB (> L2)"),
+            gpu_launches=int(lib.sfv_launch_count() - launches0),
+            roofline=dict(bound="hbm", achieved=fps / world * bpf / 1e9, peak=pk["hbm"], unit="GB/s",
+                          frac=fps / world * bpf / 1e9 / pk["hbm"], traffic=None, bytes_per_frame=bpf,
+                          note="whole-path algorithmic bytes / step time (all kernels)"))), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -191,22 +349,32 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--precision", default=os.environ.get("SFV_PRECISION", "bf16"))
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default=os.environ.get("SFV_PRECISION", "mixed"))
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 = BASELINE configs[1] (default, 512x512 batch 64); c5 = configs[4] (1024x1024 batch 16); "
+                         "c4 = configs[3] (contrastive RBVAE on 512x512 pairs, batch 256)")
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-precision", action="store_true")
+    ap.add_argument("--no-config0", action="store_true")
     args = ap.parse_args()
+    args.res = 1024 if args.config == "c5" else R
+    if args.batch is None:
+        args.batch = {"c2": BATCH, "c5": 16, "c4": 256}[args.config]
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.config == "c4":
+        return run_contrastive(args, rank, world, local)
 
     import numpy as np
     import torch
     import torch.distributed as dist
     import sfv_b200
 
+    res = args.res
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -215,25 +383,52 @@ def main():
     args.warmup = max(args.warmup, 3)
     B = args.batch
     lib = sfv_b200.lib()
-    vae, rb, sd, rsd = build_models(args.precision)
+    vae, rb, sd, rsd = build_models(args.precision, res)
     pipe = sfv_b200.FramePipeline(vae, rb, batch=B, device=dev)
+    n_in = N_INPUT_BUFFERS if res <= 512 else 3
 
     # distinct synthetic frames per rank (contiguous ranges of one long synthetic video), smooth noise
-    host = [sfv_b200.synthetic_frames(B, R, R, 1234 + 17 * (rank * N_INPUT_BUFFERS + i), smooth=True).pin_memory()
-            for i in range(N_INPUT_BUFFERS)]
+    host = [sfv_b200.synthetic_frames(B, res, res, 1234 + 17 * (rank * n_in + i), smooth=True).pin_memory()
+            for i in range(n_in)]
     devbuf = [h.to(dev) for h in host]
     words = (LATENT_DIM + 31) // 32
-    gather_codes = torch.empty(world * B, words, dtype=torch.int32, device=dev) if world > 1 else None
-    gather_lat = torch.empty(world * B, 4, R // 8, R // 8, dtype=torch.float32, device=dev) if world > 1 else None
+    lh = res // 8
+    # multi-GPU: two sets of gather buffers; this rank's kernels write its block of set i % 2 directly and the in-place
+    # all-gathers of step i run on NCCL's stream under the kernels of step i + 1
+    gath = None
+    if world > 1:
+        gath = [dict(lat=torch.empty(world * B, 4, lh, lh, dtype=torch.float32, device=dev),
+                     codes=torch.empty(world * B, words, dtype=torch.int32, device=dev),
+                     h=torch.empty(world * B, LATENT_DIM, dtype=torch.float32, device=dev), works=[]) for _ in range(2)]
+
+    def my_block(gs):
+        sl = slice(rank * B, (rank + 1) * B)
+        return sfv_b200.EncodeResult(gs["lat"][sl], gs["codes"][sl], gs["h"][sl])
+
+    def gather_async(gs):
+        gs["works"] = [sfv_b200.all_gather_slices(gs[k], rank, world, async_op=True) for k in ("lat", "codes", "h")]
+
+    def gather_wait(gs):
+        for w in gs["works"]:
+            w.wait()
+        gs["works"] = []
 
     def step_device(i):
-        r = pipe.encode_device(devbuf[i % N_INPUT_BUFFERS])
-        if world > 1:
-            dist.all_gather_into_tensor(gather_codes, r.codes)
-            dist.all_gather_into_tensor(gather_lat, r.latents)
+        if world == 1:
+            return pipe.encode_device(devbuf[i % n_in])
+        gs = gath[i % 2]
+        gather_wait(gs)                      # the gather that last read this set (step i - 2) is done
+        r = pipe.encode_device(devbuf[i % n_in], out=my_block(gs))
+        gather_async(gs)
         return r
 
+    def drain():
+        if world > 1:
+            for gs in gath:
+                gather_wait(gs)
+
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -248,6 +443,7 @@ def main():
     # ---- warm-up -------------------------------------------------------------
     for i in range(args.warmup):
         step_device(i)
+    drain()
     vae.check_async_error()
 
     # ---- timed: device-resident inputs ---------------------------------------
@@ -260,6 +456,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step_device(i)
+    drain()                                  # the last gathers are part of the job: current stream waits for them
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
@@ -273,22 +470,29 @@ def main():
     vae.check_async_error()
 
     # ---- timed: end to end from pinned host buffers ---------------------------
+    def step_e2e(i):
+        if world == 1:
+            return pipe.encode_host(host[i % n_in], reuse_output=True)    # H2D frames, kernels, D2H latents+codes+h (pinned)
+        gs = gath[i % 2]
+        gather_wait(gs)
+        r = pipe.encode_host(host[i % n_in], reuse_output=True, device_out=my_block(gs))
+        gather_async(gs)                     # latents, codes and h gathered device to device, no host round trip
+        return r
+
     for i in range(2):
-        pipe.encode_host(host[i % N_INPUT_BUFFERS])
+        step_e2e(i)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
-        res = pipe.encode_host(host[i % N_INPUT_BUFFERS], reuse_output=True)   # H2D frames, kernels, D2H latents+codes+h (pinned)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_codes, res.codes.to(dev))
+        step_e2e(i)
+    drain()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    h2d = B * R * R * 3
-    d2h = B * (4 * (R // 8) ** 2 * 4 + words * 4 + LATENT_DIM * 4)
+    h2d = B * res * res * 3
+    d2h = B * (4 * lh * lh * 4 + words * 4 + LATENT_DIM * 4)
 
     if rank != 0:
         if world > 1:
@@ -302,49 +506,60 @@ def main():
     tc = prof["tc_gemm"]
     achieved = tc["work"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
     peak = pk["tensor_sustained"]     # the kernel is timed inside a long step -> sustained figure
-    flops_frame = 1116.658466816e9 if R == 512 else None      # 2*MAC of encoder + quant_conv per 512^2 frame
+    # 2*MAC of encoder + quant_conv per frame
+    flops_frame = {512: 1116.658466816e9, 1024: 4878.95e9}.get(res)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "tc_gemm_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and res == 512:
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
 
-    # ---- parity of this very configuration vs the oracle on a bounded sample + CPU baseline ----
+    # ---- CPU baseline (the unmodified reference on a bounded sample) + parity of this very configuration ----
     cpu = None
     parity = None
+    ref = None
     if not args.no_cpu_baseline:
-        n_cpu = 2
-        fps, dt, ref = cpu_port_fps(sd, rsd, n_cpu, host[0][:n_cpu].numpy())
-        if dt < 8:                                # bounded sample: ~10-30 s of CPU work
-            n2 = min(B, max(n_cpu, int(n_cpu * 15 / dt)))
-            if n2 > n_cpu:
-                fps, dt, ref = cpu_port_fps(sd, rsd, n2, host[0][:n2].numpy())
-                n_cpu = n2
-        cpu = dict(value=fps, unit="frames/s", cores=os.cpu_count(), kind="port",
-                   sample=f"{n_cpu} frames of {R}x{R} (oracle port of the reference path, fp32, torch CPU threads={os.cpu_count()}), {dt:.1f} s")
-        # parity of this very configuration on the same frames the CPU port just encoded (checker only)
+        cores = host_threads()
+        n_cpu = PARITY_FRAMES if res <= 512 else 2
+        u8 = host[0][:n_cpu].numpy()
+        models = reference_models(sd, rsd, res)
+        _, dt_p, port = cpu_port(sd, rsd, u8)                 # checker: h for the band, and a cross-check of the reference
+        if models is not None:
+            fps, dt, ref = cpu_reference(models, u8)
+            kind, agree = "reference", port_vs_reference(ref, port)
+        else:
+            fps, dt, ref, kind, agree = n_cpu / dt_p, dt_p, port, "port", None
+        cpu = dict(value=fps, unit="frames/s", cores=cores, kind=kind,
+                   sample=f"{n_cpu} frames of {res}x{res}, fp32, torch CPU threads={cores}, {dt:.1f} s: "
+                          + ("the unmodified reference modules (oracle/_ref): AutoencoderKL.encode -> 0.18215*mode() -> "
+                             "Seq2SeqBinaryVAE.encode(hard)" if kind == "reference" else "oracle port (oracle/_ref absent)"),
+                   port_vs_reference=agree)
+        # parity of this very configuration on the same frames the CPU side just encoded (checker only)
         r = pipe.encode_device(devbuf[0][:n_cpu].contiguous())
+        vae.check_async_error()
         z = sfv_b200.unpack_codes(r.codes.cpu(), LATENT_DIM).numpy()
         diff = z != ref["z"]
-        band = np.abs(ref["h"]) < 1e-3
+        band = np.abs(port["h"]) < 1e-3
         parity = dict(latent_rel_l2=float((r.latents.cpu() - ref["lat"]).norm() / ref["lat"].norm()),
+                      latent_gate=1e-2, against=kind,
                       code_bits=int(z.size), flips_outside_band=int((diff & ~band).sum()),
-                      flips_inside_band=int((diff & band).sum()), sample_frames=n_cpu,
-                      h_maxabs=float(np.abs(r.h.cpu().numpy() - ref["h"]).max()))
+                      flips_inside_band=int((diff & band).sum()), bits_in_band=int(band.sum()),
+                      distinct_codes=int(len(np.unique(ref["z"], axis=0))), sample_frames=n_cpu,
+                      h_maxabs=float(np.abs(r.h.cpu().numpy() - port["h"]).max()))
 
-    # ---- the other 16-bit operand format on the same workload (device-resident, same timing rules) ----
+    # ---- pure bf16 operands on the same workload (device-resident, same timing rules): the known miss, recorded ----
     alt = None
-    if world == 1 and not args.no_alt_precision and args.precision in ("bf16", "fp16"):
-        ap_ = "fp16" if args.precision == "bf16" else "bf16"
+    if world == 1 and not args.no_alt_precision and args.precision in ("mixed", "bf16", "fp16"):
+        ap_ = "bf16" if args.precision != "bf16" else "mixed"
         del pipe, vae, rb
         torch.cuda.empty_cache()
-        vae2, rb2, _, _ = build_models(ap_)
+        vae2, rb2, _, _ = build_models(ap_, res)
         pipe2 = sfv_b200.FramePipeline(vae2, rb2, batch=B, device=dev)
         for i in range(3):
-            pipe2.encode_device(devbuf[i % N_INPUT_BUFFERS])
+            pipe2.encode_device(devbuf[i % n_in])
         torch.cuda.synchronize(dev)
         e0.record()
         for i in range(args.steps):
-            pipe2.encode_device(devbuf[i % N_INPUT_BUFFERS])
+            pipe2.encode_device(devbuf[i % n_in])
         e1.record()
         torch.cuda.synchronize(dev)
         alt = dict(operand_format=ap_, value=B * args.steps / (e0.elapsed_time(e1) / 1e3), unit="frames/s")
@@ -357,12 +572,14 @@ def main():
         vae2.check_async_error()
 
     line = dict(
-        metric="frames_per_sec_512x512_to_binary_code", value=value, unit="frames/s", n_gpus=world,
+        metric=f"frames_per_sec_{res}x{res}_to_binary_code", value=value, unit="frames/s", n_gpus=world,
         steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True,
-        scaling="weak", vs_baseline=None, dtype=args.precision, data="synthetic",
-        config=dict(workload=workload_name(B), frames_per_step_per_gpu=B, weights="seeded random init (no checkpoint offline)",
-                    l2_policy=f"{N_INPUT_BUFFERS} rotating input batches (> L2) and a multi-GB activation working set",
-                    operand_format=args.precision, parallelism=f"frames sharded x{world}, all_gather(codes, latents)"),
+        scaling="weak", vs_baseline=None, dtype=DTYPE_NAMES.get(args.precision, args.precision), data="synthetic",
+        config=dict(workload=workload_name(B, res), frames_per_step_per_gpu=B,
+                    weights="seeded random init (no checkpoint offline), RBVAE fc / LSTM-input gains so codes follow the frame",
+                    l2_policy=f"{n_in} rotating input batches (> L2) and a multi-GB activation working set",
+                    precision=args.precision, operand_format=OPERAND_FORMATS.get(args.precision, args.precision),
+                    parallelism=f"frames sharded x{world}" + (", async in-place all_gather(latents, codes, h) per step, double buffered" if world > 1 else "")),
         e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches),
@@ -372,7 +589,8 @@ def main():
                       kernel="tc_gemm_kernel (tcgen05 implicit GEMM: all 3x3/1x1 convs + attention GEMMs)",
                       kernel_ms_per_step=tc["ms"] / args.steps, kernel_launches_per_step=tc["launches"] / args.steps,
                       kernel_share_of_step=tc["ms"] / ms_dev if ms_dev else None,
-                      peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']}); burst {pk['tensor_burst']}",
+                      peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']}); burst {pk['tensor_burst']}; "
+                                  "fp16 and bf16 operands run at the same tcgen05 kind::f16 rate",
                       pipeline_tflops=flops_frame * value / world / 1e12 if flops_frame else None,
                       pipeline_frac_of_peak=flops_frame * value / world / 1e12 / peak if flops_frame else None),
         kernel_classes={k: dict(ms_per_step=v["ms"] / args.steps, launches_per_step=v["launches"] / args.steps,

@@ -34,7 +34,9 @@ typedef enum SfvStatus {
   SFV_ERR_CUDA = -2,       /* CUDA runtime / driver error                  */
   SFV_ERR_MISSING_KEY = -3,/* a state-dict tensor is absent or mis-shaped  */
   SFV_ERR_WORKSPACE = -4,  /* workspace too small                          */
-  SFV_ERR_DEVICE = -5      /* device-side watchdog tripped (pipeline hang) */
+  SFV_ERR_DEVICE = -5,     /* device-side watchdog tripped (pipeline hang) */
+  SFV_ERR_RANGE = -6       /* an fp16 operand left the fp16 range (MIXED / FP16 modes): results are invalid,
+                              re-create the handle with SFV_PREC_BF16 */
 } SfvStatus;
 
 /* Arithmetic mode of the encoder / GEMM operands.
@@ -42,8 +44,17 @@ typedef enum SfvStatus {
  *  BF16  : tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators,
  *          fp32 residual stream and GroupNorm statistics.
  *  FP16  : same kernels with IEEE half operands (same tensor-pipe rate,
- *          3 more mantissa bits). */
-typedef enum SfvPrecision { SFV_PREC_F32 = 0, SFV_PREC_BF16 = 1, SFV_PREC_FP16 = 2 } SfvPrecision;
+ *          3 more mantissa bits).  Diagnostic mode: conv outputs consumed directly
+ *          as operands (q, k, V, raw copies of x) saturate at +-65504.
+ *  MIXED : the product default.  fp16 where the operand is bounded by construction --
+ *          weights (per-layer power-of-two scale, undone in the epilogue), GroupNorm(+SiLU)
+ *          outputs, conv1 outputs (re-normalised by norm2) and the 16-bit copies of the
+ *          residual stream that feed Downsample / nin_shortcut (stored times 2^-6: range
+ *          +-4.19e6) -- and bf16 where range is data dependent (q, k, V^T, P, attention
+ *          output).  Every fp16 store site is range-checked on the device: a value that
+ *          leaves the fp16 range raises SFV_ERR_RANGE at the next sfv_check_async_error /
+ *          synchronising call instead of saturating silently. */
+typedef enum SfvPrecision { SFV_PREC_F32 = 0, SFV_PREC_BF16 = 1, SFV_PREC_FP16 = 2, SFV_PREC_MIXED = 3 } SfvPrecision;
 
 /* One named host tensor of a PyTorch state-dict (fp32, contiguous, reference
  * layout: conv weights OIHW, linear [out,in], LSTM [4L,L]). */
@@ -78,8 +89,9 @@ int sfv_encoder_precision(const SfvEncoder* enc);
  * slices inside one sfv_encoder_forward_* call. */
 int sfv_encoder_set_chunk(SfvEncoder* enc, int32_t frames);
 /* Synchronises `stream` and returns SFV_ERR_DEVICE if a tcgen05 pipeline
- * watchdog tripped in any kernel launched so far (bounded mbarrier waits turn a
- * would-be hang into an error). */
+ * watchdog tripped in any kernel launched so far on the current device (bounded
+ * mbarrier waits turn a would-be hang into an error), or SFV_ERR_RANGE if an fp16
+ * operand store left the fp16 range (MIXED / FP16 modes).  The flag is cleared. */
 int sfv_check_async_error(void* stream);
 
 /* Bytes of scratch sfv_encoder_forward_* needs for a batch of B frames HxW. */

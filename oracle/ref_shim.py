@@ -1,7 +1,9 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container
-only -- the GPU box has no /root/reference, so nothing that runs there may import
-this file).  TEST INFRASTRUCTURE: used by ``oracle/make_golden.py`` and by the
-CPU tests that pin the oracle against the live reference when it is present.
+"""Import the UNMODIFIED reference modules (TEST INFRASTRUCTURE): from the live /root/reference in the
+build container, else from the byte-for-byte copies ``oracle/build_ref.py`` placed under ``oracle/_ref/``
+(git-ignored, shipped to the GPU box by gpurun).  Used by ``oracle/make_golden.py``, by the CPU tests that pin
+the oracle against the reference, and by ``bench.py --impl reference`` / its ``cpu_baseline`` leg as the timed
+CPU implementation (``kind: "reference"``).  The evaluation / dataset helpers further down need files that are
+not part of the copied set and only work against the live tree.
 
 ``ldm.models.autoencoder`` imports ``pytorch_lightning`` and ``taming`` at module
 import time (autoencoder.py:2,6); neither is installed and neither is touched by
@@ -15,11 +17,25 @@ import os
 import sys
 import types
 
-REF_ROOT = "/root/reference"
+from . import build_ref
+
+LIVE_ROOT = "/root/reference"
+REF_ROOT = build_ref.root() or LIVE_ROOT
 
 
 def available() -> bool:
+    """The model classes (AutoencoderKL, both Seq2SeqBinaryVAE) can be imported."""
     return os.path.isdir(os.path.join(REF_ROOT, "src", "stable-diffusion", "ldm"))
+
+
+def live() -> bool:
+    """The whole reference tree is present (scripts, training code): build container only."""
+    return os.path.isdir(os.path.join(LIVE_ROOT, "scripts"))
+
+
+def video_path():
+    p = os.path.join(REF_ROOT, "videos", "chinchess_gettyimages-148739276-640_adpp.mp4")
+    return p if os.path.exists(p) else None
 
 
 def _install_import_stubs():
@@ -103,7 +119,7 @@ def embedding_matching_functions(flags=()):
     import numpy as np
     import torch
     import torchvision.transforms as T
-    path = os.path.join(REF_ROOT, "scripts/evaluation/state_consistency_eval/embedding_matching.py")
+    path = os.path.join(LIVE_ROOT, "scripts/evaluation/state_consistency_eval/embedding_matching.py")
     src = open(path).read()
     want = {"add_gaussian_noise", "add_occlusion", "assign_label", "calculate_state_consistency"}
     ns = {"torch": torch, "np": np, "random": random, "T": T, "flags": list(flags)}
@@ -122,7 +138,7 @@ def train_dataset_class():
     import numpy as np
     import torch
     from torch.utils.data import Dataset
-    path = os.path.join(REF_ROOT, "models/percep_RBVAE/percep_RBVAE_train.py")
+    path = os.path.join(LIVE_ROOT, "models/percep_RBVAE/percep_RBVAE_train.py")
     ns = {"torch": torch, "np": np, "random": random, "Path": Path, "Dataset": Dataset}
     for node in ast.parse(open(path).read()).body:
         if isinstance(node, ast.ClassDef) and node.name == "ShuffledStatePairDataset":

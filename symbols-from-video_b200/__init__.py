@@ -18,12 +18,13 @@ from ._lib import SfvError, lib
 from .autoencoder import (SCALE_FACTOR, KL_F8_DDCONFIG, AutoencoderKL, DiagonalGaussianDistribution,
                           FirstStage, encoder_param_shapes)
 from .rbvae import Seq2SeqBinaryVAE, hamming_matrix, unpack_codes
-from .pipeline import EncodeResult, FramePipeline, all_gather_ragged, encode_sharded, shard_range
+from .pipeline import (EncodeResult, FramePipeline, all_gather_ragged, all_gather_slices, encode_sharded,
+                       shard_range)
 from .embedding_store import (FlatEmbeddingStore, ShuffledStatePairDataset, frame_key, load_embeddings_npy,
                               lookup_embedding, save_embeddings_npy)
 from . import evaluation, ops
 from .evaluation import (add_gaussian_noise, add_occlusion, assign_label, calculate_state_consistency,
                          labels_from_flags, perturb_frames, state_consistency)
-from .weights import init_encoder_state_dict, init_rbvae_state_dict, synthetic_frames
+from .weights import init_encoder_state_dict, init_rbvae_state_dict, make_rbvae_responsive, synthetic_frames
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -16,8 +16,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfv.so")
 
-PREC_F32, PREC_BF16, PREC_FP16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_F32, "f32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_FP16, "f16": PREC_FP16}
+PREC_F32, PREC_BF16, PREC_FP16, PREC_MIXED = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_F32, "f32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_FP16, "f16": PREC_FP16,
+              "mixed": PREC_MIXED}
+DEFAULT_PRECISION = "mixed"      # fp16 for bounded operands, bf16 for attention q/k/V/P/O (include/sfv.h SfvPrecision)
 NUM_TAPS = 16
 TAP_NAMES = (["conv_in"] + [f"down.{l}.block.{b}" for l in range(4) for b in range(2)]
              + [f"down.{l}.downsample" for l in range(3)] + ["mid.block_1", "mid.attn_1", "mid.block_2", "moments"])
@@ -108,8 +110,32 @@ def require_cuda(t: torch.Tensor, what: str):
         raise SfvError(f"{what} must be a CUDA tensor: this path has no CPU fallback")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """The caller's current stream ON `device` (a tensor's device), not on whatever device happens to be current."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(t: torch.Tensor):
+    """Context manager making `t`'s device current: libsfv handles, kernel attributes and the error word are
+    per device, and the C side resolves "the device" through the CUDA current device."""
+    return torch.cuda.device(t.device)
+
+
+def run(fn, dev_tensor: torch.Tensor, *args):
+    """Call a libsfv entry point whose last parameter is the stream: `dev_tensor`'s device is made current
+    (handles, kernel attributes and the error word are per device) and ITS current stream is passed."""
+    dev = dev_tensor.device
+    with torch.cuda.device(dev):
+        check(fn(*args, stream_ptr(dev)))
+
+
+def check_async_error(device=None):
+    """Synchronise the current stream of `device` and raise SfvError if a device-side check fired since the last
+    call: a tcgen05 pipeline watchdog (outputs are garbage) or an fp16 range violation (mixed / fp16 modes).
+    Product paths call this wherever they already synchronise."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        check(lib().sfv_check_async_error(stream_ptr(dev)))
 
 
 def ptr(t):

@@ -108,13 +108,22 @@ class DiagonalGaussianDistribution(object):
         return 0.5 * torch.sum(logtwopi + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=dims)
 
 
-def _scaled_sample(post, noise, scale):
-    """scale * (mean + std * noise) (noise None -> scale * mean) on the device."""
+def _scaled_sample(post, noise, scale, out=None):
+    """scale * (mean + std * noise) (noise None -> scale * mean) on the device; `out`: optional destination
+    (e.g. this rank's slice of an all-gather buffer, so no staging copy precedes the collective)."""
+    _lib.require_cuda(post.parameters, "posterior")
     mean = post.mean.contiguous()
-    out = torch.empty_like(mean)
+    if post.deterministic:            # distributions.py:29-30: std = var = 0 -> the sample is the mean
+        noise = None
+    if out is None:
+        out = torch.empty_like(mean)
+    elif (tuple(out.shape) != tuple(mean.shape) or out.dtype != torch.float32 or out.device != mean.device
+          or not out.is_contiguous()):
+        raise ValueError("out must be a contiguous fp32 tensor shaped like the posterior mean, on its device")
     lv = post.logvar.contiguous()
-    _lib.check(_lib.lib().sfv_posterior_sample(_lib.ptr(mean), _lib.ptr(lv), _lib.ptr(noise), float(scale),
-                                               _lib.ptr(out), mean.numel(), _lib.stream_ptr()))
+    with _lib.on_device(mean):
+        _lib.check(_lib.lib().sfv_posterior_sample(_lib.ptr(mean), _lib.ptr(lv), _lib.ptr(noise), float(scale),
+                                                   _lib.ptr(out), mean.numel(), _lib.stream_ptr(mean.device)))
     return out
 
 
@@ -143,7 +152,8 @@ def _build_tree(root: nn.Module, shapes: dict):
 class AutoencoderKL(nn.Module):
     """``AutoencoderKL(ddconfig, lossconfig, embed_dim, ckpt_path=None, ignore_keys=[], ...)``
     with the reference signature (autoencoder.py:285-311).  ``precision`` is the
-    one extra knob: "bf16" (default), "fp16" or "fp32" (check mode)."""
+    one extra knob: "mixed" (default: fp16 operands where they are bounded by construction, bf16 for the
+    attention operands, every fp16 store range-checked), "bf16", "fp16" or "fp32" (check mode)."""
 
     def __init__(self, ddconfig=None, lossconfig=None, embed_dim=4, ckpt_path=None, ignore_keys=[],
                  image_key="image", colorize_nlabels=None, monitor=None, precision=None, chunk=None):
@@ -157,12 +167,13 @@ class AutoencoderKL(nn.Module):
             raise ValueError("only embed_dim=4 (kl-f8) is supported")
         self.image_key = image_key
         self.embed_dim = embed_dim
-        self.precision = (precision or os.environ.get("SFV_PRECISION", "bf16")).lower()
+        self.precision = (precision or os.environ.get("SFV_PRECISION", _lib.DEFAULT_PRECISION)).lower()
         if self.precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.chunk = chunk or int(os.environ.get("SFV_CHUNK", "0")) or None
         _build_tree(self, encoder_param_shapes())
         self._handle = None
+        self._handle_device = None
         self._ws = _lib.Workspace()
         if monitor is not None:
             self.monitor = monitor
@@ -204,12 +215,19 @@ class AutoencoderKL(nn.Module):
         except Exception:
             pass
 
-    def _native(self):
+    def _native(self, device):
+        """The native handle for `device` (weights are uploaded to the device that is current at creation;
+        one handle per device)."""
+        device = torch.device(device)
+        if self._handle is not None and self._handle_device != device:
+            self._release()
         if self._handle is None:
             table, n, keep = _lib.make_tensor_table(self.state_dict())
             h = C.c_void_p()
-            _lib.check(_lib.lib().sfv_encoder_create(table, n, _lib.PRECISIONS[self.precision], C.byref(h)))
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().sfv_encoder_create(table, n, _lib.PRECISIONS[self.precision], C.byref(h)))
             self._handle = h
+            self._handle_device = device
             if self.chunk:
                 _lib.check(_lib.lib().sfv_encoder_set_chunk(h, int(self.chunk)))
         return self._handle
@@ -217,7 +235,6 @@ class AutoencoderKL(nn.Module):
     # -- the hot path --------------------------------------------------------
     def _run(self, x, u8: bool, taps=None):
         L = _lib.lib()
-        h = self._native()
         if u8:
             B, H, W, _ = x.shape
         else:
@@ -225,6 +242,11 @@ class AutoencoderKL(nn.Module):
         if H % 8 or W % 8:
             raise ValueError(f"H and W must be multiples of 8, got {H}x{W}")
         dev = x.device
+        h = self._native(dev)
+        with torch.cuda.device(dev):
+            return self._run_on(L, h, x, u8, taps, B, H, W, dev)
+
+    def _run_on(self, L, h, x, u8, taps, B, H, W, dev):
         params = torch.empty(B, 8, H // 8, W // 8, dtype=torch.float32, device=dev)
         logvar = torch.empty(B, 4, H // 8, W // 8, dtype=torch.float32, device=dev)
         std = torch.empty_like(logvar)
@@ -235,7 +257,7 @@ class AutoencoderKL(nn.Module):
         if u8:
             _lib.check(L.sfv_encoder_forward_u8(h, _lib.ptr(x), B, H, W, _lib.ptr(params), _lib.ptr(logvar),
                                                 _lib.ptr(std), _lib.ptr(var), _lib.ptr(ws), nbytes.value,
-                                                _lib.stream_ptr()))
+                                                _lib.stream_ptr(dev)))
         else:
             tap_arr = None
             if taps is not None:
@@ -244,7 +266,7 @@ class AutoencoderKL(nn.Module):
                     tap_arr[i] = taps[i].data_ptr() if taps[i] is not None else None
             _lib.check(L.sfv_encoder_forward_nchw(h, _lib.ptr(x), B, H, W, _lib.ptr(params), _lib.ptr(logvar),
                                                   _lib.ptr(std), _lib.ptr(var), _lib.ptr(ws), nbytes.value,
-                                                  tap_arr, _lib.stream_ptr()))
+                                                  tap_arr, _lib.stream_ptr(dev)))
         return DiagonalGaussianDistribution(params, _native=(logvar, std, var))
 
     @torch.no_grad()
@@ -275,18 +297,14 @@ class AutoencoderKL(nn.Module):
         return post, dict(zip(_lib.TAP_NAMES, taps))
 
     def check_async_error(self):
-        _lib.check(_lib.lib().sfv_check_async_error(_lib.stream_ptr()))
+        """Synchronise and raise if a device-side watchdog / fp16 range check fired (see _lib.check_async_error)."""
+        _lib.check_async_error(self._handle_device)
 
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("decoder is outside the accelerated path; use encode()")
 
     def decode(self, z):
         raise NotImplementedError("decoder is outside the accelerated path")
-
-    # diffusers-style accessor named by the north star: vae.encode(x).latent_dist
-    class _EncoderOutput:
-        def __init__(self, dist):
-            self.latent_dist = dist
 
 
 def _latent_dist(self):

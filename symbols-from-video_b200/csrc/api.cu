@@ -110,13 +110,21 @@ const char* sfv_profile_log(void) {
 int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t precision, SfvEncoder** out) {
   if (!out || !tensors) return fail(SFV_ERR_INVALID, "encoder_create: null argument");
   *out = nullptr;
-  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16)
+  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16 && precision != SFV_PREC_MIXED)
     return fail(SFV_ERR_INVALID, "encoder_create: unknown precision %d", precision);
   SFV_TRY(require_device());
   SfvEncoder* e = new (std::nothrow) SfvEncoder();
   if (!e) return fail(SFV_ERR_INVALID, "out of host memory");
   e->prec = precision;
-  e->fmt = fmt_of_precision(precision);
+  if (cudaGetDevice(&e->device) != cudaSuccess) { delete e; return fail(SFV_ERR_CUDA, "cudaGetDevice failed"); }
+  e->fmt = e->fmt_w = e->fmt_attn = fmt_of_precision(precision);
+  if (precision == SFV_PREC_MIXED) {
+    // fp16 where the operand is bounded by construction, bf16 where its range is data dependent (sfv.h)
+    e->fmt = FMT_F16; e->fmt_w = FMT_F16; e->fmt_attn = FMT_BF16;
+    e->xc_scale = 1.f / 64.f;
+    e->range_check = true;
+    if (const char* v = getenv("SFV_XC_SCALE_LOG2")) e->xc_scale = ldexpf(1.f, -atoi(v));
+  }
   if (const char* v = getenv("SFV_FUSED_STATS")) e->fused_stats = atoi(v) != 0;
   if (const char* v = getenv("SFV_FUSE_NIN")) e->fuse_nin = atoi(v) != 0;
   if (const char* v = getenv("SFV_CONV_IN_TC")) e->conv_in_tc = atoi(v) != 0;
@@ -186,14 +194,18 @@ int sfv_rbvae_create_ex(const SfvTensor* tensors, int32_t n_tensors, int32_t in_
                         int32_t precision, SfvRbvae** out) {
   if (!out || !tensors) return fail(SFV_ERR_INVALID, "rbvae_create: null argument");
   *out = nullptr;
-  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16)
+  if (precision != SFV_PREC_F32 && precision != SFV_PREC_BF16 && precision != SFV_PREC_FP16 && precision != SFV_PREC_MIXED)
     return fail(SFV_ERR_INVALID, "rbvae_create: unknown precision %d", precision);
   if (in_channels < 1 || in_h < 1 || in_w < 1) return fail(SFV_ERR_INVALID, "rbvae_create: bad input shape");
   SFV_TRY(require_device());
   SfvRbvae* r = new (std::nothrow) SfvRbvae();
   if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
   r->in_channels = in_channels; r->in_h = in_h; r->in_w = in_w;
+  if (cudaGetDevice(&r->device) != cudaSuccess) { delete r; return fail(SFV_ERR_CUDA, "cudaGetDevice failed"); }
+  // MIXED: fp16 weights (scaled per layer) with bf16 activations -- the RBVAE's conv inputs are ReLU'd conv outputs,
+  // i.e. not bounded by construction, so they take the range-safe format
   r->prec = precision; r->fmt = fmt_of_precision(precision);
+  r->fmt_act = precision == SFV_PREC_MIXED ? FMT_BF16 : r->fmt;
   int st = rbvae_build(r, tensors, n_tensors);
   if (st != 0) { r->blob.release(); delete r; return st; }
   *out = r;
@@ -214,6 +226,11 @@ int sfv_rbvae_encode(SfvRbvae* r, const float* x, int32_t B, int32_t T, float in
                      float noise_ratio, float temperature, int32_t hard, float* h_out, float* z_out,
                      uint32_t* codes, void* ws, size_t ws_bytes, void* stream) {
   if (!r || !x) return fail(SFV_ERR_INVALID, "rbvae_encode: null argument");
+  {
+    int dev = -1;
+    SFV_CUDA(cudaGetDevice(&dev));
+    SFV_CHECK(dev == r->device, "rbvae: handle was created on device %d but device %d is current", r->device, dev);
+  }
   return rbvae_encode(r, x, B, T, in_scale, u, noise_ratio, temperature, hard, h_out, z_out, codes, ws, ws_bytes,
                       (cudaStream_t)stream);
 }

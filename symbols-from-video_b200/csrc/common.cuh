@@ -68,7 +68,28 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // 16-bit operand formats of the tensor-core path.
 enum : int { FMT_F16 = 0, FMT_BF16 = 1 };   // == UMMA F16F32Format encoding
-inline int fmt_of_precision(int prec) { return prec == SFV_PREC_FP16 ? FMT_F16 : FMT_BF16; }
+// single-format view of a precision (op entry points, RBVAE convs): MIXED behaves as fp16 there
+inline int fmt_of_precision(int prec) { return (prec == SFV_PREC_FP16 || prec == SFV_PREC_MIXED) ? FMT_F16 : FMT_BF16; }
+
+// ---- per-device library state ------------------------------------------------
+// One record per CUDA device ordinal: the device-side error flag (pipeline watchdog / fp16 range checks) and the SM
+// count.  Kernel attributes (cudaFuncSetAttribute is per device) are tracked by per-kernel device bit masks.
+constexpr int kMaxDevices = 64;
+struct DevState {
+  int dev = -1;
+  int* err_flag = nullptr;     // device int: 0 ok, 1..5 watchdog role code, >= kErrRangeBase fp16 range violation site
+  int num_sms = 0;
+};
+int dev_state(DevState** out);                // state of the CURRENT device (created on first use)
+constexpr int kErrRangeBase = 64;             // err_flag = kErrRangeBase + site
+enum : int { SITE_GN_OUT = 1, SITE_GN_IN = 2, SITE_XCOPY = 3 };
+// true the first time it is called for (mask, current device): the caller then sets its per-device kernel attributes
+inline bool first_use_on_device(unsigned long long& mask, int dev) {
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  if ((mask >> dev) & 1ull) return false;
+  mask |= 1ull << dev;
+  return true;
+}
 
 // ---- device helpers -------------------------------------------------------
 __device__ __forceinline__ uint16_t f32_to_16(float v, int fmt) {
@@ -148,9 +169,11 @@ int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, 
 // stats: double [N][G][2] accumulators (sum, sumsq) -- zeroed by the caller/kernel.
 int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int C, int G,
                     double* stats, cudaStream_t s);
+// fmt: 16-bit format of x (if x_is16) and of y (if y_is16).  range_check: with fmt == FMT_F16, flag 16-bit inputs /
+// outputs at the fp16 limit in the device error word (MIXED mode: saturation must not be silent).
 int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma,
                     const float* beta, void* y, int y_is16, int fmt, int N, long long HW, int C,
-                    int G, float eps, int silu, cudaStream_t s);
+                    int G, float eps, int silu, cudaStream_t s, int range_check = 0);
 int launch_zero(void* p, size_t bytes, cudaStream_t s);
 int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t s);
 int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s);
@@ -197,6 +220,12 @@ struct TcGemmArgs {
   // epilogue
   float alpha; const float* bias; const float* residual;
   float* out_f32; void* out_16; int fmt; long long ldo; int relu;
+  // fmt is the 16-bit format of A.  With fmt_split set, B and the 16-bit output carry their own formats (MIXED
+  // mode: UMMA's instruction descriptor takes a_format and b_format independently); otherwise all three are fmt.
+  int fmt_split, fmt_b, fmt_out;
+  // out_16 = to16(out16_scale * value) (0 means 1): the 16-bit copies of the residual stream are stored times 2^-6
+  // in MIXED mode; a scaled fp16 store is range-checked in the epilogue (error site SITE_XCOPY).
+  float out16_scale;
   double* gn_stats; int gn_cpg;      // optional fused GroupNorm partial sums [Nimg][Cout/gn_cpg][2] (pre-zeroed)
   // conv_in mode: instead of a 16-bit A tensor, uint8 HWC frames [Nimg][Ho][Wo][3]; the producer warp builds the
   // 3x3x3 patch rows (2u-255, zero padded, duplicated for the hi/lo weight split) straight into the swizzled A tile

@@ -59,6 +59,14 @@ void DeviceBlob::release() {
 
 // OIHW fp32 host weights -> (a) fp32 [K][Cout] for the CUDA-core kernel,
 // (b) 16-bit [Cout_pad][K] K-major rows for UMMA; k = (r*ks + s)*Cin + ci.
+float weight_scale_for(int fmt, double maxabs) {
+  if (fmt != FMT_F16 || !(maxabs > 0.0) || !std::isfinite(maxabs)) return 1.f;
+  int e = (int)floor(log2(16384.0 / maxabs));          // maxabs * 2^e in [2^13, 2^14)
+  if (e > 24) e = 24;
+  if (e < -24) e = -24;
+  return (float)ldexp(1.0, e);
+}
+
 int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Cout, int Cin, int ks,
                         int fmt, bool want16, ConvW* out) {
   out->Cin = Cin; out->Cout = Cout; out->ks = ks;
@@ -74,12 +82,16 @@ int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Co
   if (b) for (int o = 0; o < Cout; ++o) bias[o] = b[o];
   SFV_TRY(blob.upload(bias.data(), bias.size() * 4, (void**)&out->bias));
   out->w16 = nullptr;
+  out->w_scale = 1.f;
   if (want16 && Cin % 64 == 0) {
+    double mx = 0;
+    for (size_t i = 0; i < (size_t)Cout * Cin * ks * ks; ++i) mx = fmax(mx, fabs((double)w[i]));
+    const float sc = out->w_scale = weight_scale_for(fmt, mx);
     std::vector<uint16_t> w16((size_t)out->cout_pad * K, 0);
     for (int o = 0; o < Cout; ++o)
       for (int i = 0; i < Cin; ++i)
         for (int t = 0; t < ks * ks; ++t)
-          w16[(size_t)o * K + (size_t)t * Cin + i] = host_to_16(w[((size_t)o * Cin + i) * ks * ks + t], fmt);
+          w16[(size_t)o * K + (size_t)t * Cin + i] = host_to_16(w[((size_t)o * Cin + i) * ks * ks + t] * sc, fmt);
     SFV_TRY(blob.upload(w16.data(), w16.size() * 2, &out->w16));
   }
   return 0;
@@ -125,8 +137,9 @@ static int get_norm(DeviceBlob& blob, const SfvTensor* t, int n, const std::stri
   return 0;
 }
 
+// xc_scale: the fused nin_shortcut reads the 16-bit x copy, which holds xc_scale * x -> its weights carry 1 / xc_scale
 static int get_res(DeviceBlob& blob, const SfvTensor* t, int n, const std::string& name, int Cin, int Cout,
-                   int fmt, bool want16, ResW* r) {
+                   int fmt, bool want16, ResW* r, float xc_scale) {
   SFV_TRY(get_norm(blob, t, n, name + ".norm1", Cin, &r->n1));
   SFV_TRY(get_conv(blob, t, n, name + ".conv1", Cout, Cin, 3, fmt, want16, &r->c1));
   SFV_TRY(get_norm(blob, t, n, name + ".norm2", Cout, &r->n2));
@@ -144,14 +157,21 @@ static int get_res(DeviceBlob& blob, const SfvTensor* t, int n, const std::strin
       const int K = 9 * Cout + Cin;
       std::vector<uint16_t> w16((size_t)Cout * K, 0);
       std::vector<float> bias(Cout);
+      const float nin_gain = 1.f / xc_scale;
+      double mx = 0;
+      for (size_t i = 0; i < (size_t)Cout * Cout * 9; ++i) mx = fmax(mx, fabs((double)w2->host_data[i]));
+      for (size_t i = 0; i < (size_t)Cout * Cin; ++i) mx = fmax(mx, fabs((double)wn->host_data[i] * nin_gain));
+      const float sc = weight_scale_for(fmt, mx);
       for (int o = 0; o < Cout; ++o) {
         for (int i = 0; i < Cout; ++i)
           for (int tp = 0; tp < 9; ++tp)
-            w16[(size_t)o * K + (size_t)tp * Cout + i] = host_to_16(w2->host_data[((size_t)o * Cout + i) * 9 + tp], fmt);
-        for (int i = 0; i < Cin; ++i) w16[(size_t)o * K + 9 * Cout + i] = host_to_16(wn->host_data[(size_t)o * Cin + i], fmt);
+            w16[(size_t)o * K + (size_t)tp * Cout + i] = host_to_16(w2->host_data[((size_t)o * Cout + i) * 9 + tp] * sc, fmt);
+        for (int i = 0; i < Cin; ++i)
+          w16[(size_t)o * K + 9 * Cout + i] = host_to_16(wn->host_data[(size_t)o * Cin + i] * nin_gain * sc, fmt);
         bias[o] = b2->host_data[o] + bn->host_data[o];
       }
       ConvW& f = r->c2n;
+      f.w_scale = sc;
       f.Cin = Cout; f.Cout = Cout; f.ks = 3; f.cout_pad = Cout; f.extra_k = Cin;
       SFV_TRY(blob.upload(w16.data(), w16.size() * 2, &f.w16));
       SFV_TRY(blob.upload(bias.data(), bias.size() * 4, (void**)&f.bias));
@@ -162,7 +182,7 @@ static int get_res(DeviceBlob& blob, const SfvTensor* t, int n, const std::strin
 
 int encoder_build(SfvEncoder* e, const SfvTensor* t, int n) {
   const bool tc = e->prec != SFV_PREC_F32;
-  const int fmt = e->fmt;
+  const int fmt = e->fmt_w;          // every weight tensor is stored in the weight format
   // accept both "encoder.x" and "first_stage_model.encoder.x" (get_percep_embeddings.py:34-39)
   std::string pre = "";
   if (!find_tensor(t, n, "encoder.conv_in.weight") && find_tensor(t, n, "first_stage_model.encoder.conv_in.weight"))
@@ -179,15 +199,15 @@ int encoder_build(SfvEncoder* e, const SfvTensor* t, int n) {
     const int cout = 128 * mult[l];
     for (int b = 0; b < 2; ++b) {
       SFV_TRY(get_res(e->blob, t, n, p + "down." + std::to_string(l) + ".block." + std::to_string(b), cin, cout,
-                      fmt, tc, &e->down[l][b]));
+                      fmt, tc, &e->down[l][b], e->xc_scale));
       cin = cout;
     }
     if (l != 3)
       SFV_TRY(get_conv(e->blob, t, n, p + "down." + std::to_string(l) + ".downsample.conv", cin, cin, 3, fmt, tc,
                        &e->ds[l]));
   }
-  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_1", 512, 512, fmt, tc, &e->mid1));
-  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_2", 512, 512, fmt, tc, &e->mid2));
+  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_1", 512, 512, fmt, tc, &e->mid1, e->xc_scale));
+  SFV_TRY(get_res(e->blob, t, n, p + "mid.block_2", 512, 512, fmt, tc, &e->mid2, e->xc_scale));
   SFV_TRY(get_norm(e->blob, t, n, p + "mid.attn_1.norm", 512, &e->attn_norm));
   SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.q", 512, 512, 1, fmt, tc, &e->q));
   SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.k", 512, 512, 1, fmt, tc, &e->k));
@@ -251,15 +271,16 @@ static int pick_block_n(int cout_pad) {
 }
 
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
-int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
+int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats, const void* a2_16) {
+            double* gn_stats, const void* a2_16, float in_scale, float out16_scale) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
   TcGemmArgs a;
   memset(&a, 0, sizeof(a));
-  a.a = in16; a.fmt = fmt;
+  a.a = in16; a.fmt = fmt.a; a.fmt_split = 1; a.fmt_b = fmt.b; a.fmt_out = fmt.out;
+  a.out16_scale = out16_scale;
   if (stride == 1) {
     Ho = H + pad_lo + pad_hi - ks + 1; Wo = W + pad_lo + pad_hi - ks + 1;
     choose_tile(Wo, Ho, &a.BW, &a.BH);
@@ -305,7 +326,7 @@ int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int 
   a.b_row_stride = a.b_k * 2; a.b_batched = 0;
   a.Wo = Wo; a.Ho = Ho; a.Nimg = N; a.Cout = w.Cout;
   a.block_n = pick_block_n(w.cout_pad);
-  a.alpha = 1.f; a.bias = w.bias; a.residual = residual;
+  a.alpha = 1.f / (w.w_scale * in_scale); a.bias = w.bias; a.residual = residual;   // exact: both are powers of two
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
   if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
     SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
@@ -391,15 +412,20 @@ struct Fwd {
       SFV_TRY(launch_gn_stats(in, in_is16, fmt, N, HW, nw.C, 32, pl.stats, s));
       ready = pl.stats;
     }
-    return launch_gn_apply(in, in_is16, ready, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s);
+    return launch_gn_apply(in, in_is16, ready, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s,
+                           tc && e->range_check);
   }
+  // formats of a conv whose A operand is a GroupNorm / conv1 output (fmt) and whose 16-bit output is one too
+  TcFmt cf() const { return TcFmt{fmt, e->fmt_w, fmt}; }
   // operand-typed input -> fp32 stream and/or operand-typed output (+ fused GN statistics of the output)
+  // in_scale: in_op holds in_scale * x (16-bit copies of the residual stream); out_scale: same for out_op
   int conv(const ConvW& w, const void* in_op, int H, int W, int stride, const float* residual,
-           float* out_stream, void* out_op, double* stats_out) {
+           float* out_stream, void* out_op, double* stats_out, float in_scale = 1.f, float out_scale = 1.f) {
     // 3x3 s1: pad 1/1;  1x1: none;  3x3 s2 (Downsample): zero pad right/bottom only (model.py:75-77)
     const int pad_lo = (w.ks == 3 && stride == 1) ? 1 : 0;
     const int pad_hi = (w.ks == 3) ? 1 : 0;
-    if (tc) return conv_tc(w, fmt, in_op, N, H, W, stride, pad_lo, pad_hi, residual, out_stream, out_op, 0, s, stats_out);
+    if (tc) return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, residual, out_stream, out_op, 0, s, stats_out,
+                           nullptr, in_scale, out_scale);
     float* y = out_stream ? out_stream : (float*)out_op;
     return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, residual, y, 0, 1.f, s);
   }
@@ -418,17 +444,19 @@ struct Fwd {
     SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
     const float* res = x;
     void* copy = (tc && want_copy) ? pl.x16 : nullptr;
+    const float xs = e->xc_scale;              // the 16-bit copies of x hold xs * x
     if (r.has_nin && tc && e->fuse_nin) {
       // x' = nin(x) + conv2(a2): one GEMM, the 1x1 shortcut rides along as extra K chunks read from x's 16-bit copy
-      SFV_TRY(conv_tc(r.c2n, fmt, pl.oa, N, H, W, 1, 1, 1, nullptr, xo, copy, 0, s, sx(), x_op));
+      // (its weights carry 1 / xs, see get_res)
+      SFV_TRY(conv_tc(r.c2n, cf(), pl.oa, N, H, W, 1, 1, 1, nullptr, xo, copy, 0, s, sx(), x_op, 1.f, xs));
       *xo_op = copy;
       return 0;
     }
     if (r.has_nin) {
-      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr, nullptr));
+      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr, nullptr, tc ? xs : 1.f));
       res = xo;
     }
-    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy, sx()));
+    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy, sx(), 1.f, xs));
     *xo_op = tc ? copy : (const void*)xo;
     return 0;
   }
@@ -442,17 +470,18 @@ struct Fwd {
       const int Lp = (L + 7) / 8 * 8;                       // token counts need not be a multiple of 8: padded row pitch
       uint16_t* qk = (uint16_t*)pl.ob;                      // [N][L][1024]: q | k
       uint16_t* vT = (uint16_t*)pl.x16;                     // [N][512][Lp]
-      SFV_TRY(conv_tc(e->qk, fmt, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s, nullptr));
+      const int fa = e->fmt_attn;                            // q, k, V^T, P, O: range is data dependent -> bf16 in MIXED mode
+      SFV_TRY(conv_tc(e->qk, TcFmt{fmt, e->fmt_w, fa}, pl.oa, N, 1, L, 1, 0, 0, nullptr, nullptr, qk, 0, s, nullptr));
       // bias b_v is added after P V (rows of P sum to 1)
-      SFV_TRY(vT_tc(e->v, fmt, pl.oa, vT, N, L, s));
+      SFV_TRY(vT_tc(e->v, TcFmt{e->fmt_w, fmt, fa}, pl.oa, vT, N, L, s));
       uint16_t* O = (uint16_t*)pl.oa;                       // [N][L][512]  (hn is dead after the two GEMMs above)
       for (int n0 = 0; n0 < N; n0 += pl.attn_chunk) {
         const int nn = (N - n0) < pl.attn_chunk ? (N - n0) : pl.attn_chunk;
-        SFV_TRY(attention_tc(fmt, qk + (size_t)n0 * L * 1024, 1024, qk + (size_t)n0 * L * 1024 + 512, 1024,
+        SFV_TRY(attention_tc(fa, qk + (size_t)n0 * L * 1024, 1024, qk + (size_t)n0 * L * 1024 + 512, 1024,
                              vT + (size_t)n0 * C * Lp, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
                              scale, s));
       }
-      SFV_TRY(conv_tc(e->proj, fmt, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s, sx()));
+      SFV_TRY(conv_tc(e->proj, TcFmt{fa, e->fmt_w, fmt}, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s, sx()));
     } else {
       float* q = (float*)pl.ob;
       float* k = q + (size_t)N * L * C;
@@ -524,10 +553,10 @@ int attention_tc(int fmt, const void* q16, long long q_ld, const void* k16, long
 
 // V^T[n][c][token] = sum_k Wv[c][k] x[n][token][k]: the value projection computed
 // directly in the K-major layout the P V GEMM needs as its B operand.
-int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cudaStream_t s) {
+int vT_tc(const ConvW& v, TcFmt fmt, const void* x16, void* vT16, int N, int L, cudaStream_t s) {
   const int C = v.Cin;
   TcGemmArgs a; memset(&a, 0, sizeof(a));
-  a.a = v.w16; a.fmt = fmt; a.a_rank = 2;
+  a.a = v.w16; a.fmt = fmt.a; a.fmt_split = 1; a.fmt_b = fmt.b; a.fmt_out = fmt.out; a.a_rank = 2;
   a.a_dims[0] = C; a.a_dims[1] = v.cout_pad; a.a_strides[1] = (unsigned long long)C * 2;
   a.a_box[0] = 64; a.a_box[1] = 128;
   a.dim_x = 1; a.dim_y = -1; a.dim_n = -1;
@@ -535,7 +564,7 @@ int vT_tc(const ConvW& v, int fmt, const void* x16, void* vT16, int N, int L, cu
   a.b = x16; a.b_rows = L; a.b_k = C; a.b_row_stride = (unsigned long long)C * 2;
   a.b_batch_stride = (unsigned long long)L * C * 2; a.b_batched = 1;
   a.BW = 128; a.BH = 1; a.Wo = v.Cout; a.Ho = 1; a.Nimg = N; a.Cout = L; a.block_n = 256;
-  a.alpha = 1.f; a.out_16 = vT16; a.ldo = (L + 7) / 8 * 8;
+  a.alpha = 1.f / v.w_scale; a.out_16 = vT16; a.ldo = (L + 7) / 8 * 8;
   return launch_tc_gemm(a, s);
 }
 
@@ -569,6 +598,12 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
   SFV_CHECK(B >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "encoder: H, W must be multiples of 8 (got %dx%d)", H, W);
   SFV_CHECK(ws != nullptr && ws_bytes >= encoder_workspace(e, B, H, W), "encoder: workspace too small (%zu < %zu)",
             ws_bytes, encoder_workspace(e, B, H, W));
+  {
+    int dev = -1;
+    SFV_CUDA(cudaGetDevice(&dev));
+    SFV_CHECK(dev == e->device, "encoder: handle was created on device %d but device %d is current (one handle per device)",
+              e->device, dev);
+  }
   const bool tc = e->prec != SFV_PREC_F32;
   const int chunk = B < e->chunk ? B : e->chunk;
   const int h8 = H / 8, w8 = W / 8;
@@ -589,7 +624,7 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
     if (f.sx()) SFV_CUDA(cudaMemsetAsync(f.sx(), 0, sizeof(double) * 2 * 32 * N, s));
     if (tc && src_kind == SRC_NHWC_U8 && e->conv_in.w16_u8 && e->conv_in_tc && W % 8 == 0 && ((uintptr_t)xin & 3) == 0)
-      SFV_TRY(conv_in_tc(e->conv_in, e->fmt, (const unsigned char*)xin, N, H, W, f.pl.xa, f.sx(), s));
+      SFV_TRY(conv_in_tc(e->conv_in, e->fmt_w, (const unsigned char*)xin, N, H, W, f.pl.xa, f.sx(), s));
     else
       SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, f.pl.xa, f.sx(), N, H, W, s));
     SFV_TRY(tap(0, f.pl.xa, H, W));
@@ -607,7 +642,8 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
       if (l != 3) {
         // downsample output feeds down.(l+1).block.0, whose nin_shortcut (levels 1, 2) reads x directly
         const bool want_copy = tc && e->down[l + 1][0].has_nin;
-        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr, f.sx()));
+        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr, f.sx(),
+                       tc ? e->xc_scale : 1.f, e->xc_scale));
         ch /= 2; cw /= 2;
         std::swap(cur, oth);
         cur_op = tc ? (want_copy ? (const void*)f.pl.x16b : nullptr) : (const void*)cur;

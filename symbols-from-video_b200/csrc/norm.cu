@@ -74,6 +74,10 @@ __global__ void gn_stats_scalar_kernel(const float* x, long long HW, int C, int 
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
+// fp16 range check on packed pairs: bit 15 of a half of the result is set iff that half's magnitude bits are
+// >= 0x7BFF (65504 = the value a saturating conversion produces, inf, NaN).  OR-accumulated per thread.
+__device__ __forceinline__ uint32_t f16_sat_bits(uint32_t w) { return (w & 0x7FFF7FFFu) + 0x04010401u; }
+
 // GroupNorm apply (+SiLU): y = silu((x - mean_g) * rstd_g * gamma + beta).
 // A thread owns 8 consecutive channels (32 B fp32 / 16 B 16-bit in, 16 B 16-bit out) and
 // walks pixels with a 4-deep unrolled load batch so enough bytes are in flight to cover
@@ -96,10 +100,12 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, void* __restrict__ y,
                                                           int fmt, long long HW, int C, int G, float eps,
-                                                          int do_silu, int pix_per_block) {
+                                                          int do_silu, int pix_per_block, int* err) {
   __shared__ float sh_mean[64], sh_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
+  const bool chk = err != nullptr && fmt == FMT_F16;
+  uint32_t sat_in = 0, sat_out = 0;
   if (threadIdx.x < G) {
     const double cnt = (double)HW * cpg;
     const double m = stats[((long long)n * G + threadIdx.x) * 2] / cnt;
@@ -149,6 +155,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
       if (pp >= p1) break;
       float v[8];
       if (IN16) {
+        if (chk) sat_in |= f16_sat_bits(raw[u][0].x) | f16_sat_bits(raw[u][0].y) | f16_sat_bits(raw[u][0].z) | f16_sat_bits(raw[u][0].w);
         unpack2_16(raw[u][0].x, fmt, v[0], v[1]); unpack2_16(raw[u][0].y, fmt, v[2], v[3]);
         unpack2_16(raw[u][0].z, fmt, v[4], v[5]); unpack2_16(raw[u][0].w, fmt, v[6], v[7]);
       } else {
@@ -167,6 +174,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
         uint4 o;
         o.x = pack2_16(v[0], v[1], fmt); o.y = pack2_16(v[2], v[3], fmt);
         o.z = pack2_16(v[4], v[5], fmt); o.w = pack2_16(v[6], v[7], fmt);
+        if (chk) sat_out |= f16_sat_bits(o.x) | f16_sat_bits(o.y) | f16_sat_bits(o.z) | f16_sat_bits(o.w);
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + idx) = o;
       } else {
         float* o = reinterpret_cast<float*>(y) + idx;
@@ -174,6 +182,10 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
         *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
+  }
+  if (chk) {
+    if (sat_in & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_IN);
+    if (sat_out & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_OUT);
   }
 }
 
@@ -192,12 +204,14 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, void* __restrict__ y,
                                                                int fmt, long long HW, int C, int G, float eps,
-                                                               int do_silu, int pix_per_block) {
+                                                               int do_silu, int pix_per_block, int* err, int* wd_err) {
   extern __shared__ __align__(128) uint8_t ring[];
   __shared__ float sh_mean[64], sh_rstd[64];
   __shared__ __align__(8) uint64_t full[kBulkSlots];
   const int n = blockIdx.y;
   const int cpg = C / G;
+  const bool chk = err != nullptr && fmt == FMT_F16;
+  uint32_t sat_in = 0, sat_out = 0;
   constexpr int ES = IN16 ? 2 : 4;
   const int pix_bytes = C * ES;
   const int ppp = kBulkPieceBytes / pix_bytes;            // pixels per piece
@@ -247,10 +261,16 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
     const int slot = piece % kBulkSlots;
     const uint32_t bar = smem_addr(&full[slot]);
     const uint32_t parity = (uint32_t)((piece / kBulkSlots) & 1);
+    // bounded wait (~2 s): a bulk copy that never completes must surface as an error, not hang the GPU
     uint32_t done = 0;
-    while (!done) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      if (!done && (spin & 1023u) == 1023u) {
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000ull) { atomicCAS(wd_err, 0, 6); return; }
+      }
     }
     const long long pp0 = (long long)piece * ppp;
     const int cntp = (int)min((long long)ppp, (p1 - p0) - pp0);
@@ -259,6 +279,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
       float v[8];
       if (IN16) {
         const uint4 u = *reinterpret_cast<const uint4*>(buf + (r * C + tc * 8) * 2);
+        if (chk) sat_in |= f16_sat_bits(u.x) | f16_sat_bits(u.y) | f16_sat_bits(u.z) | f16_sat_bits(u.w);
         unpack2_16(u.x, fmt, v[0], v[1]); unpack2_16(u.y, fmt, v[2], v[3]);
         unpack2_16(u.z, fmt, v[4], v[5]); unpack2_16(u.w, fmt, v[6], v[7]);
       } else {
@@ -276,6 +297,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
         uint4 o;
         o.x = pack2_16(v[0], v[1], fmt); o.y = pack2_16(v[2], v[3], fmt);
         o.z = pack2_16(v[4], v[5], fmt); o.w = pack2_16(v[6], v[7], fmt);
+        if (chk) sat_out |= f16_sat_bits(o.x) | f16_sat_bits(o.y) | f16_sat_bits(o.z) | f16_sat_bits(o.w);
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + idx) = o;
       } else {
         float* o = reinterpret_cast<float*>(y) + idx;
@@ -285,6 +307,10 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
     }
     __syncthreads();                       // everyone is done reading this slot
     if (threadIdx.x == 0 && piece + kBulkSlots < npieces) issue(piece + kBulkSlots);
+  }
+  if (chk) {
+    if (sat_in & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_IN);
+    if (sat_out & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_OUT);
   }
 }
 
@@ -456,8 +482,12 @@ int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int
 
 int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma, const float* beta,
                     void* y, int y_is16, int fmt, int N, long long HW, int C, int G, float eps, int silu,
-                    cudaStream_t s) {
+                    cudaStream_t s, int range_check) {
   const int cpg = C / G;
+  DevState* ds = nullptr;
+  SFV_TRY(dev_state(&ds));
+  int* err = range_check ? ds->err_flag : nullptr;
+  int* wd = ds->err_flag;
   ProfScope prof(PROF_GN_APPLY, (double)N * HW * C * ((x_is16 ? 2 : 4) + (y_is16 ? 2 : 4)), s);
   if (C % 8 == 0 && 256 % (C / 8) == 0 && C <= 2048 && G <= 64 && C % G == 0) {
     // slabs sized so that the grid is a few waves of 148 SMs x 8 resident blocks
@@ -470,26 +500,25 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
     if (bulk < 0) { const char* e = getenv("SFV_GN_BULK"); bulk = e ? atoi(e) : 1; }
     const int pix_bytes = C * (x_is16 ? 2 : 4);
     if (bulk && kBulkPieceBytes % pix_bytes == 0 && ((uintptr_t)x & 15) == 0) {
-      static bool attr = false;
-      if (!attr) {
+      static unsigned long long attr_devs = 0;      // cudaFuncSetAttribute is per device
+      if (first_use_on_device(attr_devs, ds->dev)) {
         SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
         SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
         SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
         SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
-        attr = true;
       }
       const size_t sm = kBulkSlots * kBulkPieceBytes;
-      if (x_is16 && y_is16) gn_apply_bulk_kernel<true, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-      else if (!x_is16 && y_is16) gn_apply_bulk_kernel<false, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-      else if (x_is16 && !y_is16) gn_apply_bulk_kernel<true, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-      else gn_apply_bulk_kernel<false, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+      if (x_is16 && y_is16) gn_apply_bulk_kernel<true, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
+      else if (!x_is16 && y_is16) gn_apply_bulk_kernel<false, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
+      else if (x_is16 && !y_is16) gn_apply_bulk_kernel<true, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
+      else gn_apply_bulk_kernel<false, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
       SFV_LAUNCH_OK();
       return 0;
     }
-    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
-    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb);
+    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
+    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
+    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
+    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
   } else {
     SFV_CHECK(!x_is16 && !y_is16, "group_norm: scalar path is fp32 only");
     const long long total = (long long)N * HW * C;

@@ -124,10 +124,11 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
     if (tc) {
       // 16-bit operands for the two C->C convs (97 % of the RBVAE FLOPs) on the tcgen05 kernel;
       // conv.0 (Cin = 3 or 4) stays on CUDA cores and emits the 16-bit operand directly
-      if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 1, r->fmt, nn, h[0], w[0], in_scale, s));
-      else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt));
-      SFV_TRY(conv_tc(r->c1, r->fmt, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s));
-      SFV_TRY(conv_tc(r->c2, r->fmt, a2i, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, nullptr, 0, s));
+      const TcFmt cf{r->fmt_act, r->fmt, r->fmt_act};
+      if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 1, r->fmt_act, nn, h[0], w[0], in_scale, s));
+      else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt_act));
+      SFV_TRY(conv_tc(r->c1, cf, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s));
+      SFV_TRY(conv_tc(r->c2, cf, a2i, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, nullptr, 0, s));
     } else {
       if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 0, r->fmt, nn, h[0], w[0], in_scale, s));
       else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, a1i, 1, in_scale, s));

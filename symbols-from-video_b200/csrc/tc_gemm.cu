@@ -70,7 +70,8 @@ struct TcParams {
   const float* residual;
   float* out_f32;
   void* out_16;
-  int fmt;
+  int fmt_a, fmt_b, fmt_out;           // 16-bit formats of the A operand, the B operand and out_16
+  float out16_scale;                   // out_16 = to16(out16_scale * value); != 1 also range-checks fp16 stores
   long long ldo;
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
@@ -374,8 +375,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t base
 }
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate,
 // A/B format fmt (0 = f16, 1 = bf16), both K-major, M = 128, N = n.
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int n, int m) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc(int fmt_a, int fmt_b, int n, int m) {
+  return (1u << 4) | ((uint32_t)fmt_a << 7) | ((uint32_t)fmt_b << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
 
@@ -637,7 +638,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg) t_wait += clock64() - tw;
             if (!ok) break;
             const uint32_t tile_s = smem_u32(smem + stage * C::kStageBytes);
-            if (p.fmt == FMT_BF16) conv_in_store_rows<FMT_BF16>(v, tile_s, 4 * lane);
+            if (p.fmt_a == FMT_BF16) conv_in_store_rows<FMT_BF16>(v, tile_s, 4 * lane);
             else conv_in_store_rows<FMT_F16>(v, tile_s, 4 * lane);
             fence_proxy_async();
             __syncwarp();
@@ -727,7 +728,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, one elected lane issues; leader CTA only in pair mode) =====
     if (rank == 0) {
-      const uint32_t idesc = make_idesc(p.fmt, BLOCK_N, kBlockM * NCTA);
+      const uint32_t idesc = make_idesc(p.fmt_a, p.fmt_b, BLOCK_N, kBlockM * NCTA);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
@@ -966,7 +967,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
                     w4[q] = pack2_16(ex2_approx(fmaf(f[8 * j + 2 * q], a2, -sm_inv)),
-                                     ex2_approx(fmaf(f[8 * j + 2 * q + 1], a2, -sm_inv)), p.fmt);
+                                     ex2_approx(fmaf(f[8 * j + 2 * q + 1], a2, -sm_inv)), p.fmt_out);
                   sts128u(hb + ((j ^ sw16) << 4), w4[0], w4[1], w4[2], w4[3]);
                 }
                 fence_proxy_async();
@@ -1051,10 +1052,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int hslot = p.h16_slots == 2 ? (g_cur & 1) : 0;
               const uint32_t hb = h16_s + hslot * 2048 + lane * 64;
               if (p.out_16) {
+                if (p.out16_scale == 1.f) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts128u(hb + ((j ^ sw16) << 4), pack2_16(f[8 * j], f[8 * j + 1], p.fmt), pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt),
-                          pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt), pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt));
+                  for (int j = 0; j < 4; ++j)
+                    sts128u(hb + ((j ^ sw16) << 4), pack2_16(f[8 * j], f[8 * j + 1], p.fmt_out), pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt_out),
+                            pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt_out), pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt_out));
+                } else {
+                  // scaled 16-bit copy of the residual stream (MIXED mode: fp16 x 2^-6); a value beyond the fp16
+                  // range must not saturate silently -> error word (only the few launches that write such copies)
+                  const float s16 = p.out16_scale;
+                  float mx = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(f[j]));
+                  if (p.fmt_out == FMT_F16 && row_ok && !(mx * s16 <= 65504.f)) atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    sts128u(hb + ((j ^ sw16) << 4), pack2_16(f[8 * j] * s16, f[8 * j + 1] * s16, p.fmt_out),
+                            pack2_16(f[8 * j + 2] * s16, f[8 * j + 3] * s16, p.fmt_out),
+                            pack2_16(f[8 * j + 4] * s16, f[8 * j + 5] * s16, p.fmt_out),
+                            pack2_16(f[8 * j + 6] * s16, f[8 * j + 7] * s16, p.fmt_out));
+                }
               }
               if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[8] += t1 - tq; tq = t1; }
               fence_proxy_async();
@@ -1105,7 +1122,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (p.out_f32)
                     *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                   if (p.out_16) {
-                    uint2 u; u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                    const float s16 = p.out16_scale;
+                    if (p.fmt_out == FMT_F16 && s16 != 1.f &&
+                        !(fmaxf(fmaxf(fabsf(f[j]), fabsf(f[j + 1])), fmaxf(fabsf(f[j + 2]), fabsf(f[j + 3]))) * s16 <= 65504.f))
+                      atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
+                    uint2 u; u.x = pack2_16(f[j] * s16, f[j + 1] * s16, p.fmt_out); u.y = pack2_16(f[j + 2] * s16, f[j + 3] * s16, p.fmt_out);
                     *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0 + j) = u;
                   }
                 }
@@ -1142,7 +1163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.out_f32)
                 *reinterpret_cast<float4*>(p.out_f32 + row_off + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               if (p.out_16) {
-                uint2 u; u.x = pack2_16(f[j], f[j + 1], p.fmt); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt);
+                uint2 u; u.x = pack2_16(f[j], f[j + 1], p.fmt_out); u.y = pack2_16(f[j + 2], f[j + 3], p.fmt_out);
                 *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_16) + row_off + col0 + j) = u;
               }
             }
@@ -1190,8 +1211,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int* g_err_flag = nullptr;
-int g_num_sms = 0;
+DevState g_dev[kMaxDevices];
 int g_ncta_max = 2;     // SFV_NCTA=1 disables CTA pairs (A/B experiments)
 int g_halo = 2;         // SFV_HALO=0 disables the shared A halo box; 2 also uses it for BLOCK_N = 256 (2-stage pipeline)
 int g_epi_slots_auto = 1, g_epi_slots_r = -1, g_epi_slots_h = -1;   // SFV_EPI_SLOTS=auto|fixed|r,h
@@ -1208,11 +1228,6 @@ int tc_init() {
   SFV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess)
     return fail(SFV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  int dev = 0;
-  SFV_CUDA(cudaGetDevice(&dev));
-  SFV_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  SFV_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
-  SFV_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
   if (const char* e = getenv("SFV_NCTA")) g_ncta_max = atoi(e);
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
   if (const char* e = getenv("SFV_HALO")) g_halo = atoi(e);
@@ -1248,14 +1263,12 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
 
 template <int BLOCK_N, int NCTA, bool HALO = false>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mr, const CUtensorMap& mo32,
-               const CUtensorMap& mo16, const TcParams& p_in, cudaStream_t s, const char* tag) {
+               const CUtensorMap& mo16, const TcParams& p_in, const DevState& ds, cudaStream_t s, const char* tag) {
   using C = Cfg<BLOCK_N, NCTA, HALO>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;        // cudaFuncSetAttribute is per device
+  if (first_use_on_device(attr_devs, ds.dev))
     SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::kSmemLimit));
-    attr_set = true;
-  }
   // shared-memory plan: staging rings only where this launch needs them, the rest goes to pipeline stages
   TcParams p = p_in;
   const bool need_f32 = p.epi_mode == 1 && (p.residual || p.out_f32);
@@ -1294,7 +1307,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   p.num_stages = C::stages_for(p.res_bufs, p.h16_slots);
   SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
   const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots);
-  const int max_units = g_num_sms / NCTA;
+  const int max_units = ds.num_sms / NCTA;
   const int n_sched = p.softmax_mode ? p.n_groups : p.n_units;      // schedulable items: tiles, or whole m-tile groups
   const int grid = (n_sched < max_units ? n_sched : max_units) * NCTA;
   // algorithmic FLOPs: 2 * (valid output pixels) * Cout * K, K = taps * 64-wide chunks (no tile padding counted)
@@ -1325,8 +1338,28 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 
 }  // namespace
 
+// state of the current device, created on first use (error word, SM count)
+int dev_state(DevState** out) {
+  int dev = 0;
+  SFV_CUDA(cudaGetDevice(&dev));
+  SFV_CHECK(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+  DevState& d = g_dev[dev];
+  if (!d.err_flag) {
+    SFV_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    SFV_CUDA(cudaMalloc(&d.err_flag, sizeof(int)));
+    SFV_CUDA(cudaMemset(d.err_flag, 0, sizeof(int)));
+    d.dev = dev;
+  }
+  *out = &d;
+  return 0;
+}
+
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_TRY(tc_init());
+  DevState* dsp = nullptr;
+  SFV_TRY(dev_state(&dsp));
+  const DevState& ds = *dsp;
+  const int fmt_b = a.fmt_split ? a.fmt_b : a.fmt, fmt_out = a.fmt_split ? a.fmt_out : a.fmt;
   SFV_CHECK(a.BW * a.BH == kBlockM && (a.BW & (a.BW - 1)) == 0, "tc_gemm: bad tile %dx%d", a.BW, a.BH);
   SFV_CHECK(a.ntaps >= 1 && a.ntaps <= 9 && a.kchunks >= 1, "tc_gemm: bad taps/kchunks");
 
@@ -1359,7 +1392,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
       for (int i = 0; i < 5; ++i) { d2[i] = dims[i]; s2[i] = strides[i]; }
       d2[0] = a.a2_cin;
       s2[1] = (cuuint64_t)a.a2_cin * 2; s2[2] = s2[1] * d2[1]; s2[3] = s2[2] * d2[2]; s2[4] = s2[3] * d2[3];
-      SFV_TRY(encode_map(&ma2, a.fmt, 5, a.a2, d2, s2, box));
+      SFV_TRY(encode_map(&ma2, a.fmt, 5, a.a2, d2, s2, box));   // 16-bit data: the map's element type only matters for OOB fill (zeros)
     }
     if (halo) box[a.dim_x] = 130;
     strides[0] = 2;
@@ -1375,7 +1408,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     cuuint64_t dims[3] = {a.b_k, a.b_rows, a.b_batched ? (cuuint64_t)a.Nimg : 1};
     cuuint64_t strides[3] = {2, a.b_row_stride, a.b_batched ? a.b_batch_stride : a.b_row_stride * a.b_rows};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(a.block_n / ncta), 1};
-    SFV_TRY(encode_map(&mb, a.fmt, 3, a.b, dims, strides, box));
+    SFV_TRY(encode_map(&mb, fmt_b, 3, a.b, dims, strides, box));
   }
   if (a.u8_src) ma = ma2 = mb;          // unused by the kernel in this mode
   TcParams p;
@@ -1410,13 +1443,16 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.halo_base_offset = g_halo_boff;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
   p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
-  p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.fmt = a.fmt; p.ldo = a.ldo; p.relu = a.relu;
+  p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.ldo = a.ldo; p.relu = a.relu;
+  p.fmt_a = a.fmt; p.fmt_b = fmt_b; p.fmt_out = fmt_out;
+  p.out16_scale = a.out16_scale == 0.f ? 1.f : a.out16_scale;
+  SFV_CHECK(p.out16_scale == 1.f || !a.softmax_mode, "tc_gemm: softmax mode has no scaled 16-bit output");
   p.gn_stats = a.gn_stats; p.gn_cpg = a.gn_cpg; p.gn_groups = a.gn_cpg ? a.Cout / a.gn_cpg : 0;
   if (a.gn_stats)
     SFV_CHECK((a.gn_cpg == 4 || a.gn_cpg == 8 || a.gn_cpg == 16) && a.Cout % 32 == 0 && a.block_n >= 32 &&
                   a.block_n / a.gn_cpg <= 64,
               "tc_gemm: fused GroupNorm statistics need 4/8/16 channels per group (got %d)", a.gn_cpg);
-  p.err = g_err_flag;
+  p.err = ds.err_flag;
   // epilogue tensor maps: per-warp boxes of 32 channels x (bx x by) pixels over the output / residual tensors
   CUtensorMap mr = ma, mo32 = ma, mo16 = ma;
   const bool tma_epi = g_epi_mode == 1 && a.block_n >= 32 && a.ldo % 8 == 0 &&
@@ -1433,40 +1469,51 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     cuuint64_t st16[4] = {2, (cuuint64_t)a.ldo * 2, (cuuint64_t)a.ldo * 2 * a.Wo, (cuuint64_t)a.ldo * 2 * a.Wo * a.Ho};
     if (a.residual) SFV_TRY(encode_map(&mr, a.fmt, 4, a.residual, dims, st32, box, 128, true));
     if (a.out_f32) SFV_TRY(encode_map(&mo32, a.fmt, 4, a.out_f32, dims, st32, box, 128, true));
-    if (a.out_16) SFV_TRY(encode_map(&mo16, a.fmt, 4, a.out_16, dims, st16, box, 64, false));
+    if (a.out_16) SFV_TRY(encode_map(&mo16, fmt_out, 4, a.out_16, dims, st16, box, 64, false));
   }
   char tag[64];
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
-  if (halo && a.block_n == 256) return launch_cfg<256, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-  if (halo) return launch_cfg<128, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+  if (halo && a.block_n == 256) return launch_cfg<256, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+  if (halo) return launch_cfg<128, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
   if (ncta == 2) {
     switch (a.block_n) {
-      case 256: return launch_cfg<256, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-      case 128: return launch_cfg<128, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-      case 64: return launch_cfg<64, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-      case 32: return launch_cfg<32, 2>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+      case 256: return launch_cfg<256, 2>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+      case 128: return launch_cfg<128, 2>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+      case 64: return launch_cfg<64, 2>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+      case 32: return launch_cfg<32, 2>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
       default: break;
     }
   }
   switch (a.block_n) {
-    case 256: return launch_cfg<256, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-    case 128: return launch_cfg<128, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-    case 64: return launch_cfg<64, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-    case 32: return launch_cfg<32, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
-    case 16: return launch_cfg<16, 1>(ma, mb, ma2, mr, mo32, mo16, p, s, tag);
+    case 256: return launch_cfg<256, 1>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+    case 128: return launch_cfg<128, 1>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+    case 64: return launch_cfg<64, 1>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+    case 32: return launch_cfg<32, 1>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+    case 16: return launch_cfg<16, 1>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
     default: return fail(SFV_ERR_INVALID, "tc_gemm: unsupported block_n %d", a.block_n);
   }
 }
 
+// Synchronise `s` and read (and clear) the current device's error word.
 int tc_check_device_error(cudaStream_t s) {
-  if (!g_err_flag) return 0;
+  int dev = 0;
+  SFV_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !g_dev[dev].err_flag) { SFV_CUDA(cudaStreamSynchronize(s)); return 0; }
+  int* flag = g_dev[dev].err_flag;
   int h = 0;
-  SFV_CUDA(cudaMemcpyAsync(&h, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SFV_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   SFV_CUDA(cudaStreamSynchronize(s));
   if (h != 0) {
-    cudaMemsetAsync(g_err_flag, 0, sizeof(int), s);
+    cudaMemsetAsync(flag, 0, sizeof(int), s);
+    if (h >= kErrRangeBase) {
+      static const char* site[] = {"?", "a GroupNorm(+SiLU) output", "a conv1 output (norm2 input)",
+                                   "a 16-bit copy of the residual stream (Downsample / nin_shortcut input)"};
+      const int k = h - kErrRangeBase;
+      return fail(SFV_ERR_RANGE, "fp16 operand range exceeded at %s: the results of this call are invalid; "
+                                 "re-create the encoder with precision bf16", site[(k >= 1 && k <= 3) ? k : 0]);
+    }
     return fail(SFV_ERR_DEVICE, "tcgen05 pipeline watchdog tripped (role code %d)", h);
   }
   return 0;

@@ -54,8 +54,9 @@ def state_consistency(codes: torch.Tensor, labels: torch.Tensor, n_states: int):
         raise ValueError(f"expected codes [N,words] and labels [N], got {tuple(codes.shape)} / {tuple(labels.shape)}")
     best = torch.empty(n_states, dtype=torch.int32, device=codes.device)
     count = torch.empty(n_states, dtype=torch.int32, device=codes.device)
-    _lib.check(_lib.lib().sfv_state_consistency(_lib.ptr(codes), _lib.ptr(labels), codes.shape[0], codes.shape[1],
-                                                n_states, _lib.ptr(best), _lib.ptr(count), _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_state_consistency, codes, _lib.ptr(codes), _lib.ptr(labels), codes.shape[0], codes.shape[1],
+                                                n_states, _lib.ptr(best), _lib.ptr(count))
+    _lib.check_async_error(codes.device)     # the .cpu() below synchronises anyway: surface device-side errors here
     best = best.cpu().numpy().astype(np.int64); count = count.cpu().numpy().astype(np.int64)
     pct = [float(b) / float(c) if c > 0 else 0.0 for b, c in zip(best, count)]
     total = int(count.sum())
@@ -81,8 +82,8 @@ def perturb_frames(frames: torch.Tensor, noise=None, mean=0.0, std=0.1, occ_xy=N
             if bool((occ_xy < 0).any()) or bool((occ_xy > lim).any()):
                 raise ValueError("occlusion square outside the frame")
     out = torch.empty_like(frames) if out is None else out
-    _lib.check(_lib.lib().sfv_perturb_frames(_lib.ptr(frames), _lib.ptr(out), B, H, W, _lib.ptr(noise), float(mean),
-                                             float(std), _lib.ptr(occ_xy), int(occ_size), _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_perturb_frames, frames, _lib.ptr(frames), _lib.ptr(out), B, H, W, _lib.ptr(noise), float(mean),
+                                             float(std), _lib.ptr(occ_xy), int(occ_size))
     return out
 
 

@@ -25,9 +25,9 @@ def conv2d_nhwc(x, weight, bias, stride=1, pad=(1, 1), residual=None, relu=False
     x = x.contiguous()
     if residual is not None:
         residual = residual.contiguous()
-    _lib.check(_lib.lib().sfv_op_conv2d(_lib.ptr(x), w.ctypes.data, b.ctypes.data, _lib.ptr(residual), _lib.ptr(y),
+    _lib.run(_lib.lib().sfv_op_conv2d, x, _lib.ptr(x), w.ctypes.data, b.ctypes.data, _lib.ptr(residual), _lib.ptr(y),
                                         N, H, W, Cin, Cout, ks, stride, pad[0], pad[1], int(relu),
-                                        _lib.PRECISIONS[precision], _lib.stream_ptr()))
+                                        _lib.PRECISIONS[precision])
     return y
 
 
@@ -38,8 +38,8 @@ def conv_in_u8(frames, weight, bias, precision="fp32"):
     N, H, W, _ = frames.shape
     y = torch.empty(N, H, W, 128, dtype=torch.float32, device=frames.device)
     w = _host_f32(weight); b = _host_f32(bias)
-    _lib.check(_lib.lib().sfv_op_conv_in_u8(_lib.ptr(frames.contiguous()), w.ctypes.data, b.ctypes.data, _lib.ptr(y),
-                                            N, H, W, _lib.PRECISIONS[precision], _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_op_conv_in_u8, frames, _lib.ptr(frames.contiguous()), w.ctypes.data, b.ctypes.data, _lib.ptr(y),
+                                            N, H, W, _lib.PRECISIONS[precision])
     return y
 
 
@@ -51,8 +51,8 @@ def group_norm_nhwc(x, gamma, beta, groups=32, eps=1e-6, silu=False):
     HW = x.numel() // (N * C)
     y = torch.empty_like(x)
     g = gamma.to(x.device, torch.float32).contiguous(); b = beta.to(x.device, torch.float32).contiguous()
-    _lib.check(_lib.lib().sfv_op_group_norm(_lib.ptr(x), _lib.ptr(g), _lib.ptr(b), _lib.ptr(y), N, HW, C, groups,
-                                            float(eps), int(silu), _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_op_group_norm, x, _lib.ptr(x), _lib.ptr(g), _lib.ptr(b), _lib.ptr(y), N, HW, C, groups,
+                                            float(eps), int(silu))
     return y
 
 
@@ -62,9 +62,8 @@ def attention(q, k, v, scale=None, precision="fp32"):
     N, L, C = q.shape
     scale = C ** -0.5 if scale is None else scale
     out = torch.empty_like(q)
-    _lib.check(_lib.lib().sfv_op_attention(_lib.ptr(q.contiguous()), _lib.ptr(k.contiguous()), _lib.ptr(v.contiguous()),
-                                           _lib.ptr(out), N, L, C, float(scale), _lib.PRECISIONS[precision],
-                                           _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_op_attention, q, _lib.ptr(q.contiguous()), _lib.ptr(k.contiguous()), _lib.ptr(v.contiguous()),
+                                           _lib.ptr(out), N, L, C, float(scale), _lib.PRECISIONS[precision])
     return out
 
 
@@ -80,6 +79,6 @@ def resize_lanczos(frames, H, W, want_float=False):
     nb = C.c_size_t()
     _lib.check(_lib.lib().sfv_resize_workspace_bytes(B, Hs, Ws, H, W, C.byref(nb)))
     ws = torch.empty(nb.value, dtype=torch.uint8, device=frames.device)
-    _lib.check(_lib.lib().sfv_resize_normalise(_lib.ptr(frames), B, Hs, Ws, H, W, _lib.ptr(f), _lib.ptr(out),
-                                               _lib.ptr(ws), nb.value, _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_resize_normalise, frames, _lib.ptr(frames), B, Hs, Ws, H, W, _lib.ptr(f), _lib.ptr(out),
+                                               _lib.ptr(ws), nb.value)
     return (out, f) if want_float else out

@@ -18,6 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
+from . import _lib
 from .autoencoder import SCALE_FACTOR, AutoencoderKL, _scaled_sample
 from .rbvae import Seq2SeqBinaryVAE
 
@@ -43,6 +44,8 @@ class FramePipeline:
                  scale_factor: float = SCALE_FACTOR, device="cuda"):
         self.vae, self.rbvae, self.batch, self.scale = vae, rbvae, batch, scale_factor
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._stage = [None, None]
         self._copy_stream = None
         self._out = {}
@@ -56,13 +59,20 @@ class FramePipeline:
         return t
 
     @torch.no_grad()
-    def encode_device(self, frames_dev: torch.Tensor, noise=None, noise_ratio=0.0, U=None):
-        """One batch already resident in HBM: uint8 [B,H,W,3] cuda -> EncodeResult (on device)."""
+    def encode_device(self, frames_dev: torch.Tensor, noise=None, noise_ratio=0.0, U=None, out: EncodeResult | None = None):
+        """One batch already resident in HBM: uint8 [B,H,W,3] cuda -> EncodeResult (on device).
+
+        ``out``: preallocated destinations (latents [B,4,h,w] fp32, codes [B,words] int32, h [B,L] fp32), e.g. this
+        rank's slice of the all-gather buffers: the posterior-sample and LSTM+threshold+pack kernels write them
+        directly, so no staging copy precedes the collective."""
         post = self.vae.encode_uint8(frames_dev)
-        lat = _scaled_sample(post, noise, self.scale)
+        lat = _scaled_sample(post, noise, self.scale, out=None if out is None else out.latents)
         if self.rbvae is None:
             return EncodeResult(lat, None, None)
-        codes, h = self.rbvae.encode_codes(lat.unsqueeze(1), noise_ratio=noise_ratio, U=U)
+        B = lat.shape[0]
+        codes, h = self.rbvae.encode_codes(lat.unsqueeze(1), noise_ratio=noise_ratio, U=U,
+                                           out_codes=None if out is None else out.codes,
+                                           out_h=None if out is None or out.h is None else out.h.view(B, 1, -1))
         return EncodeResult(lat, codes, h.squeeze(1))
 
     def _pinned(self, name, shape, dtype):
@@ -73,8 +83,17 @@ class FramePipeline:
         return t
 
     @torch.no_grad()
-    def encode_host(self, frames: torch.Tensor | np.ndarray, reuse_output: bool = False):
+    def encode_host(self, frames: torch.Tensor | np.ndarray, reuse_output: bool = False,
+                    sample_posterior: bool = False, noise: torch.Tensor | None = None,
+                    device_out: EncodeResult | None = None):
         """Host uint8 frames [N,H,W,3] (ideally pinned) -> EncodeResult on the HOST.
+
+        Latents are ``scale * posterior.mode()`` by default.  ``sample_posterior=True`` stores what the
+        reference's precompute writes, ``scale * posterior.sample()`` (get_percep_embeddings.py:100-101): the
+        noise is ``noise`` ([N,4,H/8,W/8]) when given, else one ``torch.randn(1,4,h,w)`` per frame from the global
+        CPU generator, in frame order -- the draws DiagonalGaussianDistribution.sample makes (distributions.py:36).
+        ``device_out``: device tensors for all N frames that additionally receive the results (written in place by
+        the kernels, sub-batch by sub-batch) -- a rank's slice of the gather buffers in the multi-GPU driver.
 
         The frames are walked in sub-batches of ``host_batch`` (default: the encoder's chunk): the H2D copy of
         sub-batch i+1 runs on a copy stream under the kernels of sub-batch i, and each sub-batch's results go down
@@ -97,6 +116,12 @@ class FramePipeline:
         code_out = self._pinned("codes", (N, (L + 31) // 32), torch.int32) if self.rbvae is not None else None
         h_out = self._pinned("h", (N, L), torch.float32) if self.rbvae is not None else None
 
+        lh, lw = H // 8, W // 8
+        if noise is not None:
+            if tuple(noise.shape) != (N, 4, lh, lw):
+                raise ValueError(f"noise must be [N,4,H/8,W/8] = {(N, 4, lh, lw)}, got {tuple(noise.shape)}")
+            sample_posterior = True
+
         def upload(i):
             s = starts[i]
             chunk = frames[s:s + hb]
@@ -114,13 +139,25 @@ class FramePipeline:
             main.wait_event(ready[i % 2])
             if i + 1 < len(starts):
                 pending = upload(i + 1)
-            r = self.encode_device(cur)
-            consumed[i % 2].record(main)
             s0, n = starts[i], cur.shape[0]
+            nz = None
+            if sample_posterior:
+                nz = noise[s0:s0 + n] if noise is not None else torch.cat([torch.randn(1, 4, lh, lw) for _ in range(n)])
+                nz = nz.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            dst = None
+            if device_out is not None:
+                dst = EncodeResult(device_out.latents[s0:s0 + n],
+                                   None if device_out.codes is None else device_out.codes[s0:s0 + n],
+                                   None if device_out.h is None else device_out.h[s0:s0 + n])
+            r = self.encode_device(cur, noise=nz, out=dst)
+            consumed[i % 2].record(main)
             lat_out[s0:s0 + n].copy_(r.latents, non_blocking=True)
             if r.codes is not None:
                 code_out[s0:s0 + n].copy_(r.codes, non_blocking=True)
                 h_out[s0:s0 + n].copy_(r.h, non_blocking=True)
+        # synchronises, and turns a tripped pipeline watchdog / fp16 range check into an exception instead of
+        # returning garbage with status 0
+        _lib.check_async_error(self.device)
         torch.cuda.synchronize(self.device)
         if reuse_output:
             return EncodeResult(lat_out, code_out, h_out)
@@ -141,17 +178,43 @@ def all_gather_ragged(local: torch.Tensor, counts: list[int], group=None):
     return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)])
 
 
-def encode_sharded(pipe: FramePipeline, frames, rank: int, world: int, gather=True, group=None):
-    """Rank-local encode of this rank's contiguous frame range, then (optionally)
-    NCCL all-gather of latents and packed codes so every rank holds the full video."""
+def all_gather_slices(buf: torch.Tensor, rank: int, world: int, group=None, async_op: bool = False):
+    """In-place all-gather of a [world * rows, ...] buffer whose block `rank` this rank has already filled (its
+    kernels wrote there directly): no staging copy, one NCCL call.  Returns the work handle when async_op."""
+    import torch.distributed as dist
+    rows = buf.shape[0] // world
+    mine = buf[rank * rows:(rank + 1) * rows]
+    if dist.get_backend(group) != "nccl":
+        mine = mine.clone()                      # gloo (CPU tests) does not take aliased send / receive buffers
+    return dist.all_gather_into_tensor(buf, mine, group=group, async_op=async_op)
+
+
+def encode_sharded(pipe: FramePipeline, frames, rank: int, world: int, gather=True, group=None,
+                   sample_posterior: bool = False):
+    """Rank-local encode of this rank's contiguous frame range, then (optionally) an NCCL all-gather of latents,
+    packed codes and h so every rank holds the full video.  The gather buffers are allocated up front and this
+    rank's kernels write straight into its block of them (SURVEY 8e: no staging copy before the collective);
+    ragged tails are padded to the longest shard and stripped after the gather."""
     N = len(frames)
     lo, hi = shard_range(N, rank, world)
-    res = pipe.encode_host(frames[lo:hi])
     if not gather or world == 1:
-        return res, (lo, hi)
+        return pipe.encode_host(frames[lo:hi], sample_posterior=sample_posterior), (lo, hi)
     counts = [shard_range(N, r, world)[1] - shard_range(N, r, world)[0] for r in range(world)]
+    mx = max(counts)
     dev = pipe.device
-    lat = all_gather_ragged(res.latents.to(dev), counts, group)
-    codes = all_gather_ragged(res.codes.to(dev), counts, group) if res.codes is not None else None
-    h = all_gather_ragged(res.h.to(dev), counts, group) if res.h is not None else None
-    return EncodeResult(lat, codes, h), (lo, hi)
+    H, W = int(frames.shape[1]), int(frames.shape[2])
+    L = pipe.rbvae.latent_dim if pipe.rbvae is not None else 0
+    lat_g = torch.zeros(world * mx, 4, H // 8, W // 8, dtype=torch.float32, device=dev)
+    codes_g = torch.zeros(world * mx, (L + 31) // 32, dtype=torch.int32, device=dev) if L else None
+    h_g = torch.zeros(world * mx, L, dtype=torch.float32, device=dev) if L else None
+    n = hi - lo
+    mine = EncodeResult(lat_g[rank * mx:rank * mx + n], None if codes_g is None else codes_g[rank * mx:rank * mx + n],
+                        None if h_g is None else h_g[rank * mx:rank * mx + n])
+    pipe.encode_host(frames[lo:hi], reuse_output=True, sample_posterior=sample_posterior, device_out=mine)
+    works = [all_gather_slices(t, rank, world, group, async_op=True) for t in (lat_g, codes_g, h_g) if t is not None]
+    for w in works:
+        w.wait()
+
+    def strip(t):
+        return None if t is None else torch.cat([t[r * mx:r * mx + counts[r]] for r in range(world)])
+    return EncodeResult(strip(lat_g), strip(codes_g), strip(h_g)), (lo, hi)

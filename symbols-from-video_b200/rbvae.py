@@ -108,8 +108,9 @@ class Seq2SeqBinaryVAE(nn.Module):
         except Exception:
             pass
 
-    def _native(self, H, W):
-        key = (H, W)
+    def _native(self, H, W, device=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        key = (H, W, device)
         if key not in self._handles:
             fin = self.channels * _down3(H) * _down3(W)
             have = self.encoder_cnn.fc.weight.shape[1]
@@ -119,14 +120,16 @@ class Seq2SeqBinaryVAE(nn.Module):
                                    f"{H}x{W} input vs fc.in_features {have}")
             table, n, keep = _lib.make_tensor_table(self.state_dict())
             h = C.c_void_p()
-            _lib.check(_lib.lib().sfv_rbvae_create_ex(table, n, self.in_channels, H, W,
-                                                      _lib.PRECISIONS[self.precision], C.byref(h)))
+            with torch.cuda.device(device):       # weights land on `device`: one handle per (shape, device)
+                _lib.check(_lib.lib().sfv_rbvae_create_ex(table, n, self.in_channels, H, W,
+                                                          _lib.PRECISIONS[self.precision], C.byref(h)))
             self._handles[key] = h
         return self._handles[key]
 
     # -- the hot path --------------------------------------------------------
     @torch.no_grad()
-    def _encode(self, x, temperature, hard, noise_ratio, U=None, in_scale=1.0, want_codes=False):
+    def _encode(self, x, temperature, hard, noise_ratio, U=None, in_scale=1.0, want_codes=False, out_codes=None,
+                out_h=None):
         _lib.require_cuda(x, "Seq2SeqBinaryVAE input")
         if x.dim() != 5:
             raise ValueError(f"expected [B,T,C,H,W], got {tuple(x.shape)}")
@@ -134,7 +137,7 @@ class Seq2SeqBinaryVAE(nn.Module):
         if Cc != self.in_channels:
             raise ValueError(f"expected {self.in_channels} channels, got {Cc}")
         L = self.latent_dim
-        h = self._native(H, W)
+        h = self._native(H, W, x.device)
         x = x.to(torch.float32).contiguous()
         dev = x.device
         if U is None:
@@ -145,25 +148,37 @@ class Seq2SeqBinaryVAE(nn.Module):
                 U = None
         if U is not None:
             U = U.to(device=dev, dtype=torch.float32).reshape(B * T, L).contiguous()
-        h_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)
+        words = (L + 31) // 32
+        for t, shape, dt, what in ((out_h, (B, T, L), torch.float32, "out_h"), (out_codes, (B * T, words), torch.int32, "out_codes")):
+            if t is not None and (tuple(t.shape) != shape or t.dtype != dt or t.device != dev or not t.is_contiguous()):
+                raise ValueError(f"{what} must be a contiguous {dt} tensor of shape {shape} on {dev}")
+        h_seq = out_h if out_h is not None else torch.empty(B, T, L, dtype=torch.float32, device=dev)
         z_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)
-        codes = torch.empty(B * T, (L + 31) // 32, dtype=torch.int32, device=dev) if want_codes else None
+        codes = out_codes if out_codes is not None else (
+            torch.empty(B * T, words, dtype=torch.int32, device=dev) if want_codes else None)
         nbytes = C.c_size_t()
         lib = _lib.lib()
         _lib.check(lib.sfv_rbvae_workspace_bytes(h, B * T, C.byref(nbytes)))
         ws = self._ws.get(nbytes.value, dev)
-        _lib.check(lib.sfv_rbvae_encode(h, _lib.ptr(x), B, T, float(in_scale), _lib.ptr(U), float(noise_ratio),
-                                        float(temperature), int(bool(hard)), _lib.ptr(h_seq), _lib.ptr(z_seq),
-                                        _lib.ptr(codes), _lib.ptr(ws), nbytes.value, _lib.stream_ptr()))
+        _lib.run(lib.sfv_rbvae_encode, x, h, _lib.ptr(x), B, T, float(in_scale), _lib.ptr(U), float(noise_ratio),
+                 float(temperature), int(bool(hard)), _lib.ptr(h_seq), _lib.ptr(z_seq),
+                 _lib.ptr(codes), _lib.ptr(ws), nbytes.value)
         return z_seq, h_seq, codes
+
+    def check_async_error(self, device=None):
+        """Synchronise and raise if a device-side watchdog / range check fired (the 16-bit modes run the two
+        C->C convs on the tcgen05 kernel, whose pipeline waits are bounded)."""
+        _lib.check_async_error(device)
 
     def encode(self, x, temperature=0.5, hard=False, noise_ratio=0.1, U=None):
         """percep_RBVAE_model.py:172-191: x [B,T,C,H,W] -> z_seq [B,T,L]."""
         return self._encode(x, temperature, hard, noise_ratio, U)[0]
 
-    def encode_codes(self, x, temperature=0.5, noise_ratio=0.0, U=None, in_scale=1.0):
-        """hard code, bit-packed: (codes uint32-as-int32 [B*T, ceil(L/32)], h_seq [B,T,L])."""
-        _, h_seq, codes = self._encode(x, temperature, True, noise_ratio, U, in_scale, want_codes=True)
+    def encode_codes(self, x, temperature=0.5, noise_ratio=0.0, U=None, in_scale=1.0, out_codes=None, out_h=None):
+        """hard code, bit-packed: (codes uint32-as-int32 [B*T, ceil(L/32)], h_seq [B,T,L]).  out_codes / out_h:
+        optional destinations the LSTM+threshold+pack kernel writes directly (a rank's slice of a gather buffer)."""
+        _, h_seq, codes = self._encode(x, temperature, True, noise_ratio, U, in_scale, want_codes=True,
+                                       out_codes=out_codes, out_h=out_h)
         return codes, h_seq
 
     def forward(self, x, temperature=1.0, hard=False, noise_ratio=0.1, U=None):
@@ -185,6 +200,6 @@ def hamming_matrix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _lib.require_cuda(a, "codes")
     a = a.contiguous(); b = b.contiguous()
     out = torch.empty(a.shape[0], b.shape[0], dtype=torch.int32, device=a.device)
-    _lib.check(_lib.lib().sfv_hamming(_lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0], a.shape[1],
-                                      _lib.ptr(out), _lib.stream_ptr()))
+    _lib.run(_lib.lib().sfv_hamming, a, _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0], a.shape[1],
+                                      _lib.ptr(out))
     return out

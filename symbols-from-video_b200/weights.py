@@ -80,6 +80,22 @@ def init_rbvae_state_dict(in_channels, latent_dim, feat_hw, channels=256, num_la
     return sd
 
 
+def make_rbvae_responsive(sd: dict, fc_gain: float = 40.0, bias_gain: float = 0.02, ih_gain: float = 4.0) -> dict:
+    """Default-init RBVAE weights give ONE constant code whatever the frame (the LSTM biases decide every sign;
+    per-bit std of h across frames ~5e-6), so a code comparison on them proves nothing.  No trained checkpoint
+    exists offline; this rescaling -- boost ``fc`` and the LSTM input weights, damp the fc / LSTM
+    biases -- makes the code follow the frame (distinct codes per frame, a populated |h| < 1e-3 band), which is
+    what the bench / smoke parity lines need.  Same recipe as the chinchess fixture (oracle/chinchess.py)."""
+    out = dict(sd)
+    out["encoder_cnn.fc.weight"] = sd["encoder_cnn.fc.weight"] * fc_gain
+    for k in list(sd):
+        if "bias" in k and ("lstm" in k or k.endswith("fc.bias")):
+            out[k] = sd[k] * bias_gain
+        if "weight_ih" in k:
+            out[k] = sd[k] * ih_gain
+    return out
+
+
 def synthetic_frames(n, H, W, seed=1234, smooth=False) -> torch.Tensor:
     """SURVEY 8d synthetic inputs: i.i.d. uniform uint8 [n,H,W,3], or a low-pass-filtered variant
     (GroupNorm / softmax statistics on white noise are atypical)."""

@@ -3,15 +3,15 @@ tools/gpu_diag.py (one subprocess per check, results to gpurun_out/diag.json).
 
 Every check drives the product through its public Python mirror, i.e. through
 the C ABI of libsfv.so, and compares with the CPU oracle on the same seeded
-inputs.  Tolerances (stated per check):
-  fp32 check mode : latent mean/logvar rel-L2 <= 1e-4               (north star)
-  fp16 operands   : latent mean rel-L2 <= 1e-2                        (north star gate)
-  bf16 operands   : latent mean rel-L2 <= max(1e-2, 1.25 x numerics-model floor);
-                    the floor itself (bf16 operand rounding with everything else
-                    exact) is 0.8-1.4e-2 on random-init weights, see oracle/numerics_model.py
-  codes           : bit-exact wherever the oracle's |h + noise| >= 1e-3; flips inside
-                    the band are counted and reported
-  integer work    : bit-exact (resize, bit-packing, Hamming)
+inputs.  Tolerances are the north star's, with no implementation-fitted clause:
+  fp32 check mode       : latent mean / logvar / std / var rel-L2 <= 1e-4
+  16-bit operand modes  : latent mean rel-L2 <= 1e-2 -- "mixed" (the product default) and "fp16" meet it with
+                          ~5x margin; pure "bf16" operands do NOT on random-init weights (operand-rounding floor
+                          0.9-1.6e-2, oracle/numerics_model.py): its cases assert the same 1e-2 and are marked
+                          xfail (known miss, recorded) in tests/test_gpu_parity.py
+  codes                 : bit-exact wherever the oracle's |h + noise| >= 1e-3 in EVERY mode; flips inside
+                          the band are counted and reported
+  integer work          : bit-exact (resize, bit-packing, Hamming)
 """
 from __future__ import annotations
 
@@ -42,6 +42,11 @@ def r16(t, prec):
     return t.to(torch.bfloat16 if prec == "bf16" else torch.float16).float()
 
 
+def latent_gate(prec):
+    """North-star latent gate: 1e-4 in the fp32 check mode, 1e-2 for every 16-bit operand mode."""
+    return 1e-4 if prec == "fp32" else 1e-2
+
+
 # ------------------------------------------------------------------ single ops
 def check_conv(prec, N, H, W, Cin, Cout, ks=3, stride=1, pad=(1, 1), residual=False, relu=False, seed=0):
     g = torch.Generator().manual_seed(seed)
@@ -51,6 +56,7 @@ def check_conv(prec, N, H, W, Cin, Cout, ks=3, stride=1, pad=(1, 1), residual=Fa
     Ho = (H + pad[0] + pad[1] - ks) // stride + 1
     Wo = (W + pad[0] + pad[1] - ks) // stride + 1
     res = torch.randn(N, Cout, Ho, Wo, generator=g) if residual else None
+    # fp16 weights are stored times a per-layer power of two (exact), so plain fp16 rounding models them
     xe, we = (x, w) if prec == "fp32" else (r16(x, prec), r16(w, prec))
     ref = F.conv2d(F.pad(xe, (pad[0], pad[1], pad[0], pad[1])), we, b, stride=stride)
     if residual:
@@ -166,18 +172,16 @@ def check_encoder_golden(prec, name):
     # uint8-fed entry point must agree with the float entry point (same arithmetic, fused gather)
     post8 = vae.encode_uint8(torch.from_numpy(u8).to(DEV))
     out["u8_vs_float_maxabs"] = float((post8.parameters - post.parameters).abs().max())
-    if prec == "fp32":
-        assert out["mean"] <= 1e-4 and out["logvar"] <= 1e-4, out
-        assert out["u8_vs_float_maxabs"] == 0.0, out
-    else:
-        floor = numerics_model.encode_moments(x, sd, prec)
+    if prec != "fp32":
+        floor = numerics_model.encode_moments(x, sd, prec)        # recorded: where the error comes from
         out["floor_mean"] = rel_l2(floor[:, :4], g["mean"])
         out["vs_model_mean"] = rel_l2(post.mean, floor[:, :4])
-        out["meets_1e-2"] = bool(out["mean"] <= 1e-2)
-        if prec == "fp16":
-            assert out["mean"] <= 1e-2, out
-        else:
-            assert out["mean"] <= max(1e-2, 1.25 * out["floor_mean"]), out
+    tol = latent_gate(prec)
+    out["gate"] = tol
+    # the posterior's four tensors (distributions.py:24-33): mean, clamped logvar, std = exp(0.5 lv), var = exp(lv)
+    assert out["mean"] <= tol and out["logvar"] <= tol and out["std"] <= tol and out["var"] <= tol, out
+    if prec == "fp32":
+        assert out["u8_vs_float_maxabs"] == 0.0, out
     return out
 
 
@@ -196,7 +200,7 @@ def check_encoder_taps(prec, seed=0, B=1, H=64, W=64):
         else:
             r = taps_ref[name]
         out[name] = rel_l2(t.permute(0, 3, 1, 2), r)
-    tol = 1e-4 if prec == "fp32" else 3e-2
+    tol = latent_gate(prec)
     bad = {k: v for k, v in out.items() if not (v <= tol)}
     assert not bad, dict(prec=prec, bad=bad, all=out)
     return out
@@ -288,7 +292,8 @@ def check_rbvae_tensor_core(name, prec):
     o, i, n = code_flips(z, g["z_hard"], g["h"])
     out = dict(case=name, prec=prec, h_maxabs=float(np.abs(h - g["h"]).max()), h_scale=float(np.abs(g["h"]).max()),
                flips_outside=o, flips_inside=i, band=n, bits=int(z.size))
-    assert out["h_maxabs"] < (2e-3 if prec == "bf16" else 3e-4), out
+    assert out["h_maxabs"] < (3e-4 if prec == "fp16" else 2e-3), out     # mixed: fp16 weights, bf16 activations
+    assert o == 0, out                   # bit-exact outside the |h| < 1e-3 band in every mode
     return out
 
 
@@ -326,10 +331,8 @@ def check_pipeline(prec="fp16", B=6, R=64, L=25, seed=0, batch=4):
     o, i, n = code_flips(z, z_ref[:, 0].numpy(), h_ref[:, 0].numpy())
     out = dict(prec=prec, latent_rel_l2=rel_l2(res.latents, lat_ref), h_maxabs=float((res.h - h_ref[:, 0]).abs().max()),
                flips_outside=o, flips_inside=i, band=n, bits=int(z.size))
-    tol = 1e-4 if prec == "fp32" else 2e-2
-    assert out["latent_rel_l2"] <= tol, out
-    if prec == "fp32":
-        assert o == 0, out
+    assert out["latent_rel_l2"] <= latent_gate(prec), out
+    assert o == 0, out
     return out
 
 
@@ -362,7 +365,7 @@ def check_native_frame_size(prec="fp16"):
     out = dict(prec=prec, mean=rel_l2(post.mean, ref.mean), logvar=rel_l2(post.logvar, ref.logvar),
                shape=list(post.mean.shape))
     assert out["shape"] == [1, 4, 88, 160]
-    assert out["mean"] <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), out
+    assert out["mean"] <= latent_gate(prec), out
     # native RBVAE shape (fc = 256*11*20) on the resulting latent
     rsd = orb.init_state_dict(4, 25, (11, 20), seed=3)
     rb = sfv_b200.Seq2SeqBinaryVAE(in_channels=4, out_channels=4, latent_dim=25, hidden_dim=25)   # reference defaults
@@ -373,6 +376,7 @@ def check_native_frame_size(prec="fp16"):
                               return_h=True)
     o, i, n = code_flips(z, z_ref.numpy(), h_ref.numpy())
     out.update(flips_outside=o, flips_inside=i, band=n)
+    assert o == 0, out
     return out
 
 
@@ -409,8 +413,7 @@ def check_contrastive_512(prec="fp32"):
     out = dict(prec=prec, h_maxabs=float((hh.cpu() - h).abs().max()), flips_outside=o, flips_inside=i, band=n,
                bits=int(zz.size))
     assert out["h_maxabs"] < (2e-5 if prec == "fp32" else 2e-3), out
-    if prec == "fp32":
-        assert o == 0, out
+    assert o == 0, out
     return out
 
 
@@ -438,11 +441,11 @@ def check_chinchess_video(prec="fp32"):
                h_maxabs=float(np.abs(res.h.cpu().numpy() - g["h"]).max()), flips_outside=o, flips_inside=i,
                band=n, bits=int(z.size), distinct_codes=int(len(np.unique(z, axis=0))),
                distinct_codes_ref=int(len(np.unique(g["z_hard"], axis=0))))
-    assert out["latent_rel_l2"] <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), out
+    assert out["latent_rel_l2"] <= latent_gate(prec), out
+    assert o == 0, out                            # every mode: no flip outside the |h| < 1e-3 band
+    assert out["distinct_codes"] >= 20, out       # the fixture's codes follow the frame (27 in the reference)
     if prec == "fp32":
-        assert o == 0 and out["h_maxabs"] < 1e-5, out
-    else:
-        assert o <= (0.002 if prec == "fp16" else 0.02) * z.size, out      # reported, see DESIGN 2
+        assert out["h_maxabs"] < 1e-5, out
     return out
 
 
@@ -533,10 +536,68 @@ def check_state_consistency_pipeline(prec="fp32"):
         w_ref, p_ref = oev.state_consistency(zs, labels.numpy(), len(flags) + 1)
         o, i_, n = code_flips(sfv_b200.unpack_codes(codes, L).cpu().numpy(), zs, hs)
         out[str(kind)] = dict(weighted=w, weighted_ref=w_ref, flips_outside=o, flips_inside=i_, band=n)
-        if prec == "fp32":
-            assert o == 0, out
-            if i_ == 0:
-                assert abs(w - w_ref) < 1e-12 and np.allclose(pct, p_ref), out
+        assert o == 0, out
+        if i_ == 0:
+            assert abs(w - w_ref) < 1e-12 and np.allclose(pct, p_ref), out
+    return out
+
+
+def check_range_safety():
+    """MIXED mode must not saturate silently.  The residual stream is driven far beyond the fp16
+    limit by scaling conv_in (GroupNorm makes everything downstream scale invariant, so the oracle stays well
+    conditioned):  (a) stream max ~3e5 > 65504: the 16-bit x copies are stored times 2^-6, so mixed still meets the
+    1e-2 gate and raises nothing;  (b) stream max ~3e8 > 65504 * 64: the epilogue's range check must turn the
+    overflow into SfvError (SFV_ERR_RANGE) instead of returning saturated latents, and bf16 must still pass (a);
+    (c) a GroupNorm gamma of 1e6 pushes a GroupNorm+SiLU output beyond 65504: the apply pass must flag it."""
+    out = {}
+    u8 = frames.synthetic_frames(2, 64, 64, 5, smooth=True)
+    x = frames.normalise_u8(u8)
+
+    def scaled(gain, gamma_gain=1.0):
+        sd = kl_f8.init_state_dict(0)
+        sd["encoder.conv_in.weight"] = sd["encoder.conv_in.weight"] * gain
+        sd["encoder.conv_in.bias"] = sd["encoder.conv_in.bias"] * gain
+        sd["encoder.down.1.block.0.norm2.weight"] = sd["encoder.down.1.block.0.norm2.weight"] * gamma_gain
+        return sd
+
+    def run(prec, sd):
+        vae = sfv_b200.AutoencoderKL(precision=prec)
+        vae.load_state_dict(sd)
+        post = vae.encode(x.to(DEV))
+        vae.check_async_error()
+        return post
+
+    # (a) 3e5: beyond plain fp16, inside the scaled copy's range
+    sd = scaled(2e5)
+    taps = {}
+    ref = kl_f8.encode(x, sd, taps)
+    out["stream_max_a"] = float(taps["down.0.block.1"].abs().max())
+    assert out["stream_max_a"] > 65504.0, out
+    out["mixed_a"] = rel_l2(run("mixed", sd).mean, ref.mean)
+    assert out["mixed_a"] <= 1e-2, out
+    # (b) 3e8: beyond the scaled copy's range -> loud failure in mixed, bf16 unaffected
+    sd = scaled(2e8)
+    ref = kl_f8.encode(x, sd)
+    try:
+        run("mixed", sd)
+        out["mixed_b"] = "no error"
+    except sfv_b200.SfvError as e:
+        out["mixed_b"] = str(e)[:120]
+    assert "range exceeded" in out["mixed_b"], out
+    out["bf16_b"] = rel_l2(run("bf16", sd).mean, ref.mean)
+    assert out["bf16_b"] <= 3e-2, out
+    # (c) GroupNorm output beyond 65504
+    sd = scaled(1.0, gamma_gain=1e6)
+    try:
+        run("mixed", sd)
+        out["mixed_c"] = "no error"
+    except sfv_b200.SfvError as e:
+        out["mixed_c"] = str(e)[:120]
+    assert "range exceeded" in out["mixed_c"], out
+    # the error word is cleared by the failing check: a healthy run afterwards is clean
+    sd = kl_f8.init_state_dict(0)
+    out["after"] = rel_l2(run("mixed", sd).mean, kl_f8.encode(x, sd).mean)
+    assert out["after"] <= 1e-2, out
     return out
 
 
@@ -555,7 +616,7 @@ def check_conv_in_tensor_core(prec="fp16"):
         y32 = sfv_b200.ops.conv_in_u8(dev8, w, b, precision="fp32")
         r = dict(layer=rel_l2(y, ref), layer_cuda_core=rel_l2(y32, ref), layer_maxabs=float((y.cpu() - ref).abs().max()))
         # hi+lo split keeps ~16 (bf16) / ~22 (fp16) bits of w/255; A is exact
-        assert r["layer"] <= (3e-5 if prec == "bf16" else 2e-6), (B, H, W, r)
+        assert r["layer"] <= (3e-5 if prec == "bf16" else 2e-6), (B, H, W, r)   # mixed = fp16 weights here
         if H >= 64:
             a = vae.encode_uint8(dev8).parameters.clone()
             c = vae.encode(frames.normalise_u8(u8).to(DEV)).parameters.clone()
@@ -582,7 +643,7 @@ def check_odd_token_count(prec="fp16"):
         vae.check_async_error()
         ref = kl_f8.encode(x, sd)
         out[f"{B}x{H}x{W}"] = dict(mean=rel_l2(got.mean, ref.mean), logvar=rel_l2(got.logvar, ref.logvar))
-        assert out[f"{B}x{H}x{W}"]["mean"] <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), out
+        assert out[f"{B}x{H}x{W}"]["mean"] <= latent_gate(prec), out
     return out
 
 
@@ -603,7 +664,7 @@ def check_shape_sweep(prec="fp16"):
         out[f"{B}x{H}x{W}"] = e
         worst = max(worst, e)
         assert torch.isfinite(got.parameters).all(), (B, H, W)
-        assert e <= (1e-4 if prec == "fp32" else 1e-2 if prec == "fp16" else 2.5e-2), (B, H, W, e)
+        assert e <= latent_gate(prec), (B, H, W, e)
     out["worst"] = worst
     return out
 
@@ -611,12 +672,12 @@ def check_shape_sweep(prec="fp16"):
 def check_edge_cases():
     """Empty / minimal / ragged inputs and error behaviour at the boundary."""
     import pytest
-    vae, sd = make_vae("bf16", 0)
+    vae, sd = make_vae("mixed", 0)
     out = {}
     # smallest legal frame (8x8 -> 1x1 latent, one attention token): tensor-core and fp32 modes both run it
     ref8 = kl_f8.encode(torch.zeros(1, 3, 8, 8), sd)
-    out["tiny_8x8_bf16"] = rel_l2(vae.encode(torch.zeros(1, 3, 8, 8, device=DEV)).mean, ref8.mean)
-    assert out["tiny_8x8_bf16"] < 2.5e-2, out
+    out["tiny_8x8_mixed"] = rel_l2(vae.encode(torch.zeros(1, 3, 8, 8, device=DEV)).mean, ref8.mean)
+    assert out["tiny_8x8_mixed"] <= 1e-2, out
     v32, _ = make_vae("fp32", 0)
     p = v32.encode(torch.zeros(1, 3, 8, 8, device=DEV))
     ref = kl_f8.encode(torch.zeros(1, 3, 8, 8), sd)

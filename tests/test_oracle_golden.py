@@ -167,7 +167,7 @@ def test_flop_count_matches_survey():
 
 
 # ---- live reference (build container only) -----------------------------------
-@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+@pytest.mark.skipif(not ref_shim.available(), reason="neither /root/reference nor oracle/_ref present")
 def test_oracle_matches_live_reference_encoder():
     sd = kl_f8.init_state_dict(3)
     m = ref_shim.autoencoder_kl(sd)
@@ -180,7 +180,7 @@ def test_oracle_matches_live_reference_encoder():
     assert torch.allclose(z, 0.18215 * p.mode())
 
 
-@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+@pytest.mark.skipif(not ref_shim.available(), reason="neither /root/reference nor oracle/_ref present")
 def test_oracle_matches_live_reference_rbvae():
     sd = rbvae.init_state_dict(4, 32, (11, 20), seed=11)
     m = ref_shim.rbvae("percep", 4, 32, sd)          # native hard-wired 88x160 shape, unmodified module
@@ -229,7 +229,7 @@ def test_evaluation_oracle_matches_reference_golden():
     np.testing.assert_allclose(pct, g["percentages"], atol=1e-12)
 
 
-@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+@pytest.mark.skipif(not ref_shim.live(), reason="needs the live /root/reference tree (scripts / training code)")
 def test_evaluation_oracle_matches_live_reference():
     import random
     import torchvision.transforms as T
@@ -250,7 +250,7 @@ def test_evaluation_oracle_matches_live_reference():
     assert [ns["assign_label"](i, [4, 9]) for i in (0, 3, 4, 8, 9, 100)] == [0, 0, 1, 1, 2, 2]
 
 
-@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+@pytest.mark.skipif(not ref_shim.live(), reason="needs the live /root/reference tree (scripts / training code)")
 def test_resident_pair_dataset_matches_live_reference():
     """sfv_b200.ShuffledStatePairDataset (HBM-resident mirror) vs the reference class, other seed/segments."""
     import random
