@@ -213,10 +213,63 @@ def dataset_case():
     print("dataset:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 
 
+def precompute_case(n_frames=96, target=(128, 72)):
+    """The reference's embedding precompute (get_percep_embeddings.py:76-114) on the first frames of its sample
+    video: per frame, in frame order, ``load_img``'s arithmetic on the decoded frame (RGB, LANCZOS to `target`,
+    LANCZOS again to multiples of 32, /255, NCHW, 2x-1; :54-71 -- executed from the reference's own source text
+    with ``Image.open(path)`` replaced by the in-memory frame), ``encode_first_stage`` (= first_stage_model.encode,
+    ddpm.py:861-863) and ``get_first_stage_encoding`` (= scale_factor * posterior.sample(), ddpm.py:542-549) with
+    the global RNG seeded ``torch.manual_seed(0)`` once before the loop; keys are the extractor's ``%010d.jpg``.
+    ``LatentDiffusion`` itself cannot be imported here (omegaconf / CLIP), its two methods are the one-liners above.
+    Stored: keys, the embedding dict's dtype/shape, per-frame latent sums, a few whole latents, and the codes / h a
+    percep RBVAE (chinchess weights) gives on those sampled latents."""
+    import ast
+    import cv2
+    import PIL
+    from PIL import Image
+    path = os.path.join(ref_shim.LIVE_ROOT, "src/stable-diffusion/get_percep_embeddings.py")
+    fn = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "load_img"][0]
+    src_lines = open(path).read().splitlines()[fn.lineno - 1:fn.end_lineno]
+    body = "\n".join(src_lines).replace('Image.open(path).convert("RGB")', 'path.convert("RGB")')
+    body = body.replace("target_size = (1280, 720)", f"target_size = {tuple(target)!r}")
+    ns = {"Image": Image, "PIL": PIL, "np": np, "torch": torch, "print": lambda *a, **k: None}
+    exec(body, ns)
+    load_img = ns["load_img"]
+    cap = cv2.VideoCapture(ref_shim.video_path())
+    sd = kl_f8.init_state_dict(0)
+    m = ref_shim.autoencoder_kl(sd)
+    rsd, (fh, fw) = chinchess.rbvae_weights()
+    L = chinchess.L
+    rb = ref_shim.rbvae("percep", 4, L, rsd, feat_hw=(fh, fw))
+    emb = {}
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for i in range(n_frames):
+            ok, f = cap.read()
+            assert ok
+            img = load_img(Image.fromarray(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)))
+            encoded = m.encode(img)                                  # encode_first_stage
+            latent = 0.18215 * encoded.sample()                      # get_first_stage_encoding
+            emb["{:010d}.jpg".format(i)] = latent.cpu().numpy()
+    keys = list(emb.keys())
+    lat = np.concatenate([emb[k] for k in keys])
+    with torch.no_grad():
+        z = torch.from_numpy(lat)
+        zs = rb.encode(z.unsqueeze(1), temperature=0.5, hard=True, noise_ratio=0.0)[:, 0].numpy()
+        hs = rb.encoder_rnn(rb.encoder_cnn(z).reshape(-1, 1, L))[0][:, 0].numpy()
+    np.savez_compressed(os.path.join(OUT, "precompute_chinchess.npz"), keys=np.array(keys), target=np.array(target),
+                        item_shape=np.array(emb[keys[0]].shape), item_dtype=str(emb[keys[0]].dtype),
+                        latent_sum=lat.astype(np.float64).sum(axis=(1, 2, 3)), latents_head=lat[:4], latents_tail=lat[-2:],
+                        h=hs, z_hard=zs, noise_seed=0)
+    print("precompute:", len(keys), emb[keys[0]].shape, emb[keys[0]].dtype, "distinct codes", len(np.unique(zs, axis=0)))
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-precompute" in sys.argv:
+        return precompute_case()
     if "--only-chinchess" in sys.argv:
         return chinchess_case()
     if "--only-evaluation" in sys.argv:
@@ -235,6 +288,7 @@ def main():
     chinchess_case()
     evaluation_case()
     dataset_case()
+    precompute_case()
 
 
 if __name__ == "__main__":

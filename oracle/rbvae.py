@@ -46,8 +46,8 @@ def lstm_forward(x_seq, sd, prefix="encoder_rnn.lstm."):
         w_ih, w_hh = sd[prefix + f"weight_ih_l{l}"], sd[prefix + f"weight_hh_l{l}"]
         b_ih, b_hh = sd[prefix + f"bias_ih_l{l}"], sd[prefix + f"bias_hh_l{l}"]
         Hd = w_hh.shape[1]
-        h = torch.zeros(B, Hd, dtype=x_seq.dtype)
-        c = torch.zeros(B, Hd, dtype=x_seq.dtype)
+        h = torch.zeros(B, Hd, dtype=x_seq.dtype, device=x_seq.device)
+        c = torch.zeros(B, Hd, dtype=x_seq.dtype, device=x_seq.device)
         outs = []
         for t in range(T):
             gates = F.linear(layer_in[:, t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
@@ -69,7 +69,8 @@ def binary_concrete(logits, temperature=0.5, hard=False, noise_ratio=0.1, U=None
     ``torch.rand`` draw so that both sides can consume the same uniform tensor;
     with noise_ratio == 0 the result does not depend on U."""
     if U is None:
-        U = torch.rand(logits.shape)
+        U = torch.rand(logits.shape)                 # the reference draws on the CPU (:33)
+    U = U.to(logits.device)
     y = torch.sigmoid((logits + logistic_noise(U, noise_ratio, eps)) / temperature)
     if hard:
         y_hard = (y > 0.5).float()

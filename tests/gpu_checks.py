@@ -353,6 +353,60 @@ def check_full_size_properties(prec="bf16", B=4, R=512):
     return out
 
 
+def cuda_oracle(fn, *tensors_and_dicts):
+    """Run an oracle function on the GPU in true fp32 (TF32 off) -- the fast high-precision reference SURVEY 8(c)
+    prescribes for shapes the CPU oracle takes minutes on.  Still the oracle's code, only the device differs."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return fn(*tensors_and_dicts)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def check_full_size_oracle(prec="mixed", R=512, B=4, L=25):
+    """BASELINE configs[1] / configs[4] frame sizes against the ORACLE (not just properties): the oracle runs on the
+    GPU in fp32 with TF32 disabled, after being pinned against its own CPU run on a small frame in this very check.
+    Latent gate as everywhere; RBVAE codes (responsive weights, so they differ per frame) bit-exact outside the band."""
+    sd = kl_f8.init_state_dict(0)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    out = dict(prec=prec, R=R, B=B)
+    # pin the CUDA-fp32 oracle on a case the CPU oracle does in a second
+    xs = frames.normalise_u8(frames.synthetic_frames(2, 64, 96, 3, smooth=True))
+    out["cuda_oracle_vs_cpu_oracle"] = rel_l2(cuda_oracle(kl_f8.encode_moments, xs.to(DEV), sd_dev), kl_f8.encode_moments(xs, sd))
+    assert out["cuda_oracle_vs_cpu_oracle"] <= 2e-5, out
+    vae = sfv_b200.AutoencoderKL(precision=prec)
+    vae.load_state_dict(sd)
+    u8 = frames.synthetic_frames(B, R, R, 11, smooth=True)
+    x = frames.normalise_u8(u8)
+    ref = torch.cat([cuda_oracle(kl_f8.encode_moments, x[i:i + 1].to(DEV), sd_dev) for i in range(B)])   # frame by frame: 16k^2 scores
+    post = vae.encode_uint8(torch.from_numpy(u8).to(DEV))
+    vae.check_async_error()
+    refp = kl_f8.Posterior(ref)
+    out.update(mean=rel_l2(post.mean, refp.mean), logvar=rel_l2(post.logvar, refp.logvar), std=rel_l2(post.std, refp.std),
+               var=rel_l2(post.var, refp.var))
+    tol = latent_gate(prec)
+    assert max(out["mean"], out["logvar"], out["std"], out["var"]) <= tol, out
+    # codes on top (responsive RBVAE weights), oracle RBVAE also on the GPU in fp32
+    fh = R // 64
+    rsd = sfv_b200.make_rbvae_responsive(orb.init_state_dict(4, L, (fh, fh), seed=1), 100.0, 0.002, 8.0)
+    rsd_dev = {k: v.to(DEV) for k, v in rsd.items()}
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, L, L, input_hw=(R // 8, R // 8), precision=prec)
+    rb.load_state_dict(rsd)
+    lat = sfv_b200.FirstStage(vae).get_first_stage_mode(post)
+    codes, h = rb.encode_codes(lat[:, None])
+    z_ref, h_ref = cuda_oracle(lambda a, b: orb.encode(a, b, hard=True, noise_ratio=0.0, return_h=True),
+                               (kl_f8.SCALE_FACTOR * refp.mean)[:, None], rsd_dev)
+    z = sfv_b200.unpack_codes(codes, L).cpu().numpy()
+    o, i, n = code_flips(z, z_ref[:, 0].cpu().numpy(), h_ref[:, 0].cpu().numpy())
+    out.update(flips_outside=o, flips_inside=i, band=n, distinct_codes=int(len(np.unique(z, axis=0))),
+               h_maxabs=float((h[:, 0] - h_ref[:, 0]).abs().max()))
+    assert o == 0, out
+    return out
+
+
 def check_native_frame_size(prec="fp16"):
     """The reference's native frame size 1280x704 (get_percep_embeddings.py:60-66): non-square, W not a
     power of two, 14080 attention tokens; one frame against the CPU oracle (about 15 s of CPU)."""
@@ -446,6 +500,98 @@ def check_chinchess_video(prec="fp32"):
     assert out["distinct_codes"] >= 20, out       # the fixture's codes follow the frame (27 in the reference)
     if prec == "fp32":
         assert out["h_maxabs"] < 1e-5, out
+    return out
+
+
+def check_precompute_driver(prec="mixed"):
+    """one call turns the reference's sample video into the reference's ``*_perceps.npy``.
+    (a) the reference's own precompute flow on the first 96 frames (tests/golden/precompute_chinchess.npz, minted by
+        oracle/make_golden.precompute_case from get_percep_embeddings.py's load_img + encode_first_stage +
+        get_first_stage_encoding under torch.manual_seed(0)): keys / item shape / dtype equal, latents within the
+        gate, RBVAE codes on them bit-exact outside the band;
+    (b) all 480 frames, mode(), the fixture's crop variant, three decode threads, resumable part files: codes equal
+        the chinchess golden; a second run resumes every block from its part file and returns the same arrays."""
+    import tempfile
+    from oracle import ref_shim
+    video = ref_shim.video_path()
+    assert video is not None, "oracle/_ref/videos/chinchess*.mp4 missing (run __graft_entry__.build() in the build container)"
+    g = np.load(os.path.join(GOLDEN, "precompute_chinchess.npz"))
+    vae, sd = make_vae(prec, 0)
+    rsd, _ = chinchess.rbvae_weights()
+    H, W = chinchess.HW
+    L = chinchess.L
+    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, L, L, input_hw=(H // 8, W // 8), precision=prec)
+    rb.load_state_dict(rsd)
+    src = sfv_b200.VideoSource(video)
+    out = dict(prec=prec)
+    with tempfile.TemporaryDirectory() as tmp:
+        npy = os.path.join(tmp, "chinchess_perceps.npy")
+        torch.manual_seed(int(g["noise_seed"]))
+        res = sfv_b200.precompute_embeddings(src, vae, rb, target_size=tuple(int(v) for v in g["target"]), batch=32,
+                                             frame_range=(0, len(g["keys"])), sample_posterior=True, out_npy=npy,
+                                             out_flat=os.path.join(tmp, "flat"))
+        emb = np.load(npy, allow_pickle=True).item()                 # how percep_RBVAE_train.py:204 reads it
+        assert list(emb.keys()) == [str(k) for k in g["keys"]]
+        first = emb[str(g["keys"][0])]
+        assert first.shape == tuple(g["item_shape"]) and str(first.dtype) == str(g["item_dtype"]), (first.shape, first.dtype)
+        lat = np.concatenate([emb[str(k)] for k in g["keys"]])
+        flat = sfv_b200.FlatEmbeddingStore.load(os.path.join(tmp, "flat"))
+        assert np.array_equal(np.asarray(flat.latents), lat) and flat.keys == list(emb.keys())
+        out["a_latent_rel_l2"] = rel_l2(np.concatenate([lat[:4], lat[-2:]]), np.concatenate([g["latents_head"], g["latents_tail"]]))
+        out["a_sum_maxabs"] = float(np.abs(lat.astype(np.float64).sum(axis=(1, 2, 3)) - g["latent_sum"]).max())
+        z = sfv_b200.unpack_codes(res.codes, L).numpy()
+        o, i, n = code_flips(z, g["z_hard"], g["h"])
+        out.update(a_flips_outside=o, a_flips_inside=i, a_band=n, a_stats={k: v for k, v in res.stats.items() if "fps" in k})
+        assert out["a_latent_rel_l2"] <= latent_gate(prec), out
+        assert o == 0, out
+        # (b) whole video, fixture variant, parallel decode, resumable
+        gold = np.load(os.path.join(GOLDEN, "chinchess_480x64x128.npz"))
+        parts = os.path.join(tmp, "parts")
+        kw = dict(target_size=(W, 72), batch=64, sample_posterior=False, fit="crop", n_decoders=3, part_dir=parts,
+                  part_frames=128)
+        r1 = sfv_b200.precompute_embeddings(src, vae, rb, **kw)
+        z1 = sfv_b200.unpack_codes(r1.codes, L).numpy()
+        o, i, n = code_flips(z1, gold["z_hard"], gold["h"])
+        out.update(b_frames=len(r1.keys), b_flips_outside=o, b_flips_inside=i,
+                   b_latent_sum_maxabs=float(np.abs(r1.latents.double().sum(dim=(1, 2, 3)).numpy() - gold["latent_sum"]).max()),
+                   b_stats={k: v for k, v in r1.stats.items() if "fps" in k or k == "resumed_blocks"})
+        assert len(r1.keys) == 480 and r1.keys[479] == "0000000479.jpg" and o == 0, out
+        r2 = sfv_b200.precompute_embeddings(src, vae, rb, **kw)
+        out["b_resumed_blocks"] = r2.stats["resumed_blocks"]
+        assert r2.stats["resumed_blocks"] == 4 and r2.stats["frames_encoded_now"] == 0, out
+        assert torch.equal(r1.latents, r2.latents) and torch.equal(r1.codes, r2.codes), out
+        # a killed job: one part file missing -> only that block is recomputed
+        os.remove(os.path.join(parts, "part-0000000128-0000000256.npz"))
+        r3 = sfv_b200.precompute_embeddings(src, vae, rb, **kw)
+        assert r3.stats["resumed_blocks"] == 3 and r3.stats["frames_encoded_now"] == 128 and torch.equal(r3.codes, r1.codes), out
+    return out
+
+
+def check_resident_dataset():
+    """SURVEY 8 f1 on the device: the HBM-resident ShuffledStatePairDataset serves the items the reference class
+    produced (tests/golden/dataset.npz, same toy embeddings as oracle/make_golden.dataset_case), both straight from
+    the pickled dict and from a FlatEmbeddingStore written to disk, memory-mapped and moved to the GPU."""
+    import random
+    import tempfile
+    g = np.load(os.path.join(GOLDEN, "dataset.npz"))
+    segs = [tuple(int(v) for v in s) for s in g["segments"]]
+    gen = torch.Generator().manual_seed(9)
+    lat = torch.randn(160, 4, 2, 3, generator=gen).numpy()
+    emb = {(f"{i:010d}.jpg" if i % 3 else f"{i:010d}"): lat[i:i + 1] for i in range(160)}
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        sfv_b200.FlatEmbeddingStore.from_pickled(emb).save(os.path.join(tmp, "flat"))
+        for src_name, src in (("pickled", emb), ("flat_mmap", os.path.join(tmp, "flat"))):
+            for mode in ("train", "val", "test"):
+                random.seed(31)
+                ds = sfv_b200.ShuffledStatePairDataset(src, segs, test_pct=0.15, val_pct=0.1, mode=mode, device=DEV)
+                assert random.random() == float(g[mode + "_rand_after"])
+                items = torch.stack([ds[i] for i in range(len(ds))])
+                assert items.is_cuda and ds.store.latents.is_cuda
+                ok = np.array_equal(items.cpu().numpy(), g[mode + "_items"])
+                out[f"{src_name}/{mode}"] = dict(items=int(items.shape[0]), equal=bool(ok))
+                assert ok, out
+                assert torch.equal(ds.batch(list(range(len(ds)))), items)
     return out
 
 

@@ -148,3 +148,18 @@ def test_edge_cases_and_errors():
 
 def test_mixed_mode_never_saturates_silently():
     print(_c().check_range_safety())
+
+
+@pytest.mark.parametrize("prec", ["mixed", "fp32"])
+def test_precompute_driver_video_to_reference_npy(prec):
+    print(_c().check_precompute_driver(prec))
+
+
+def test_resident_dataset_on_device():
+    print(_c().check_resident_dataset())
+
+
+@pytest.mark.parametrize("prec,R,B", [("mixed", 512, 4), ("fp32", 512, 1), ("mixed", 1024, 2), ("fp32", 1024, 1),
+                                      pytest.param("bf16", 512, 4, marks=BF16_MISS.marks)])
+def test_full_size_against_cuda_fp32_oracle(prec, R, B):
+    print(_c().check_full_size_oracle(prec, R, B))
