@@ -51,7 +51,7 @@ typedef enum SfvStatus {
  *          outputs, conv1 outputs (re-normalised by norm2) and the 16-bit copies of the
  *          residual stream that feed Downsample / nin_shortcut (stored times 2^-6: range
  *          +-4.19e6) -- and bf16 where range is data dependent (q, k, V^T, P, attention
- *          output).  Every fp16 store site is range-checked on the device: a value that
+ *          output, and proj_out's weights: a tcgen05 GEMM takes both operands in one format).  Every fp16 store site is range-checked on the device: a value that
  *          leaves the fp16 range raises SFV_ERR_RANGE at the next sfv_check_async_error /
  *          synchronising call instead of saturating silently. */
 typedef enum SfvPrecision { SFV_PREC_F32 = 0, SFV_PREC_BF16 = 1, SFV_PREC_FP16 = 2, SFV_PREC_MIXED = 3 } SfvPrecision;

@@ -123,7 +123,9 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
     e->fmt = FMT_F16; e->fmt_w = FMT_F16; e->fmt_attn = FMT_BF16;
     e->xc_scale = 1.f / 64.f;
     e->range_check = true;
+    e->stream16 = true;
     if (const char* v = getenv("SFV_XC_SCALE_LOG2")) e->xc_scale = ldexpf(1.f, -atoi(v));
+    if (const char* v = getenv("SFV_STREAM16")) e->stream16 = atoi(v) != 0;    // A/B: 0 keeps the fp32 residual stream
   }
   if (const char* v = getenv("SFV_FUSED_STATS")) e->fused_stats = atoi(v) != 0;
   if (const char* v = getenv("SFV_FUSE_NIN")) e->fuse_nin = atoi(v) != 0;

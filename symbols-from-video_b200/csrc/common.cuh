@@ -160,8 +160,10 @@ struct IgemmArgs {
   int nchw_out;              // write y as NCHW [N,Cout,Ho,Wo] instead
 };
 int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
+// y16 != nullptr: write to16(y16_scale * value) there (format fmt16) instead of the fp32 y
 int launch_conv_in(const void* x, int src_kind, const float* w, const float* bias, float* y, double* stats,
-                   int N, int H, int W, cudaStream_t s);
+                   int N, int H, int W, cudaStream_t s, void* y16 = nullptr, int fmt16 = 0, float y16_scale = 1.f);
+int launch_16_to_f32_scaled(const void* x, float* y, long long n, int fmt, float mul, cudaStream_t s);
 int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, int y16, int fmt, int N, int H, int W,
                     float in_scale, cudaStream_t s);
 
@@ -173,7 +175,8 @@ int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int
 // outputs at the fp16 limit in the device error word (MIXED mode: saturation must not be silent).
 int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma,
                     const float* beta, void* y, int y_is16, int fmt, int N, long long HW, int C,
-                    int G, float eps, int silu, cudaStream_t s, int range_check = 0);
+                    int G, float eps, int silu, cudaStream_t s, int range_check = 0, float in_mul = 1.f);
+// in_mul: x holds (true value) / in_mul (the 16-bit residual stream of MIXED mode is stored times 2^-6 -> in_mul = 64)
 int launch_zero(void* p, size_t bytes, cudaStream_t s);
 int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t s);
 int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s);
@@ -183,12 +186,13 @@ int launch_head(const float* moments_nhwc8, float* params, float* logvar, float*
                 int N, int HW, cudaStream_t s);
 int launch_sample(const float* mean, const float* logvar, const float* noise, float scale,
                   float* out, long long n, cudaStream_t s);
-int launch_lstm_code(const float* logits, int B, int T, int L, int layers,
+// logits: [B*T][L] (splits == 0) or the fc split-K partials [splits][B*T][L] + fc_bias (summed in the kernel's load)
+int launch_lstm_code(const float* logits, int splits, const float* fc_bias, int B, int T, int L, int layers,
                      const float* w_ih, const float* w_hh, const float* bias,
                      const float* u, float noise_ratio, float temperature, int hard,
                      float* h_out, float* z_out, uint32_t* codes, cudaStream_t s);
-int launch_fc(const float* x, const float* w, const float* bias, float* y, int N, long long K,
-              int L, float* partial, int splits, cudaStream_t s);
+void fc_plan(long long K, int L, int* KS, int* splits);
+int launch_fc(const float* x, const float* w, float* partial, int N, long long n_stride, long long K, int L, cudaStream_t s);
 int launch_hamming(const uint32_t* a, int Na, const uint32_t* b, int Nb, int words, int* out,
                    cudaStream_t s);
 int launch_state_consistency(const uint32_t* codes, const int* labels, long long n, int words, int n_states,
@@ -218,7 +222,9 @@ struct TcGemmArgs {
   int Wo, Ho, Nimg, Cout;
   int block_n;
   // epilogue
-  float alpha; const float* bias; const float* residual;
+  float alpha; const float* bias;
+  const void* residual;              // fp32 [.., ldo], or with res16 a 16-bit tensor (format fmt_out) added as res_mul * value
+  int res16; float res_mul;
   float* out_f32; void* out_16; int fmt; long long ldo; int relu;
   // fmt is the 16-bit format of A.  With fmt_split set, B and the 16-bit output carry their own formats (MIXED
   // mode: UMMA's instruction descriptor takes a_format and b_format independently); otherwise all three are fmt.

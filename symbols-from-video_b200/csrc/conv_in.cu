@@ -19,7 +19,8 @@ constexpr int TH = 8, TW = 32;
 template <int SRC>
 __global__ void __launch_bounds__(256, 1)
 conv_in_kernel(const void* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-               float* __restrict__ y, double* __restrict__ stats, int H, int W, int tiles_x, int tiles) {
+               float* __restrict__ y, double* __restrict__ stats, int H, int W, int tiles_x, int tiles,
+               uint16_t* __restrict__ y16, int fmt16, float y16_scale) {
   __shared__ float patch[TH + 2][TW + 2][3];
   __shared__ float red[8][32][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,7 +57,8 @@ conv_in_kernel(const void* __restrict__ x, const float* __restrict__ w, const fl
     __syncthreads();
     const int oy = y0 + warp;
     if (oy < H) {
-      float* yrow = y + (((long long)n * H + oy) * W + x0) * 128 + lane * 4;
+      const long long row0 = (((long long)n * H + oy) * W + x0) * 128 + lane * 4;
+      float* yrow = y + row0;
 #pragma unroll 2
       for (int px = 0; px < TW; ++px) {
         if (x0 + px >= W) break;
@@ -72,7 +74,12 @@ conv_in_kernel(const void* __restrict__ x, const float* __restrict__ w, const fl
               a0 = fmaf(v, wr[k][0], a0); a1 = fmaf(v, wr[k][1], a1);
               a2 = fmaf(v, wr[k][2], a2); a3 = fmaf(v, wr[k][3], a3);
             }
-        *reinterpret_cast<float4*>(yrow + (long long)px * 128) = make_float4(a0, a1, a2, a3);
+        if (y16) {        // 16-bit (scaled) residual stream: one coalesced 256-byte row per pixel
+          uint2 u; u.x = pack2_16(a0 * y16_scale, a1 * y16_scale, fmt16); u.y = pack2_16(a2 * y16_scale, a3 * y16_scale, fmt16);
+          *reinterpret_cast<uint2*>(y16 + row0 + (long long)px * 128) = u;
+        } else {
+          *reinterpret_cast<float4*>(yrow + (long long)px * 128) = make_float4(a0, a1, a2, a3);
+        }
         s_sum += (a0 + a1) + (a2 + a3);
         s_sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
       }
@@ -171,16 +178,16 @@ int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, 
 // x: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W]; w: fp32 [27][128]; y: fp32 NHWC [N,H,W,128];
 // stats_or_null: fp64 [N][32][2] (pre-zeroed) receives sum / sum of squares per GroupNorm group.
 int launch_conv_in(const void* x, int src_kind, const float* w, const float* bias, float* y, double* stats,
-                   int N, int H, int W, cudaStream_t s) {
+                   int N, int H, int W, cudaStream_t s, void* y16, int fmt16, float y16_scale) {
   SFV_CHECK(src_kind == SRC_NHWC_U8 || src_kind == SRC_NCHW_F32, "conv_in: unsupported source layout");
   SFV_CHECK(N <= 65535, "conv_in: batch too large");
   const int tiles_x = ceil_div(W, TW), tiles = tiles_x * ceil_div(H, TH);
   const int gx = tiles < 160 ? tiles : 160;
   ProfScope prof(PROF_IGEMM, 2.0 * N * (double)H * W * 128 * 27, s);
   if (src_kind == SRC_NHWC_U8)
-    conv_in_kernel<SRC_NHWC_U8><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles);
+    conv_in_kernel<SRC_NHWC_U8><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles, (uint16_t*)y16, fmt16, y16_scale);
   else
-    conv_in_kernel<SRC_NCHW_F32><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles);
+    conv_in_kernel<SRC_NCHW_F32><<<dim3(gx, N), 256, 0, s>>>(x, w, bias, y, stats, H, W, tiles_x, tiles, (uint16_t*)y16, fmt16, y16_scale);
   SFV_LAUNCH_OK();
   return 0;
 }

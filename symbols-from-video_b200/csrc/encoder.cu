@@ -212,7 +212,9 @@ int encoder_build(SfvEncoder* e, const SfvTensor* t, int n) {
   SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.q", 512, 512, 1, fmt, tc, &e->q));
   SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.k", 512, 512, 1, fmt, tc, &e->k));
   SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.v", 512, 512, 1, fmt, tc, &e->v));
-  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.proj_out", 512, 512, 1, fmt, tc, &e->proj));
+  // proj_out's A operand is the attention output (fmt_attn); tcgen05 kind::f16 takes A and B in ONE 16-bit format (a
+  // descriptor with a_format != b_format faults as an illegal instruction on B200), so its weights follow fmt_attn
+  SFV_TRY(get_conv(e->blob, t, n, p + "mid.attn_1.proj_out", 512, 512, 1, e->fmt_attn, tc, &e->proj));
   {  // fused q|k projection: one GEMM with N = 1024
     const SfvTensor* qw = find_tensor(t, n, p + "mid.attn_1.q.weight");
     const SfvTensor* kw = find_tensor(t, n, p + "mid.attn_1.k.weight");
@@ -272,8 +274,8 @@ static int pick_block_n(int cout_pad) {
 
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
-            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats, const void* a2_16, float in_scale, float out16_scale) {
+            int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
+            double* gn_stats, const void* a2_16, float in_scale, float out16_scale, int res16, float res_mul) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
@@ -327,6 +329,7 @@ int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, in
   a.Wo = Wo; a.Ho = Ho; a.Nimg = N; a.Cout = w.Cout;
   a.block_n = pick_block_n(w.cout_pad);
   a.alpha = 1.f / (w.w_scale * in_scale); a.bias = w.bias; a.residual = residual;   // exact: both are powers of two
+  a.res16 = res16; a.res_mul = res_mul;
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
   if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
     SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
@@ -337,7 +340,7 @@ int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, in
 
 // conv_in on the tensor pipe, fed from uint8 HWC frames (see the weight preparation in encoder_build)
 int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, int W, float* out_f32, double* gn_stats,
-               cudaStream_t s) {
+               cudaStream_t s, void* out_16, int fmt_out, float out16_scale) {
   SFV_CHECK(w.w16_u8 != nullptr, "conv_in_tc: no uint8 weights");
   TcGemmArgs a;
   memset(&a, 0, sizeof(a));
@@ -349,6 +352,7 @@ int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, i
   a.Wo = W; a.Ho = H; a.Nimg = N; a.Cout = 128; a.block_n = 128;
   a.alpha = 1.f / kConvInScale; a.bias = w.bias;
   a.out_f32 = out_f32; a.ldo = 128;
+  if (out_16) { a.out_16 = out_16; a.fmt_split = 1; a.fmt_b = fmt; a.fmt_out = fmt_out; a.out16_scale = out16_scale; }
   if (gn_stats) { a.gn_stats = gn_stats; a.gn_cpg = 4; }      // caller zeroed the accumulators
   return launch_tc_gemm(a, s);
 }
@@ -372,23 +376,26 @@ int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, 
 namespace {
 
 struct Plan {
-  float *xa, *xb;
+  void *xa, *xb;            // residual stream ping-pong: fp32, or (stream16) 16-bit scaled
   void *oa, *ob, *x16, *x16b;
   double* stats; double* stats2;
   float* S; void* P; float* moments;
   int attn_chunk;
 };
 
-void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
+void make_plan(bool tc, bool s16, int Bc, int H, int W, Arena& ar, Plan* p) {
   const size_t E0 = (size_t)Bc * H * W * 128;
   const size_t osz = tc ? 2 : 4;
   const size_t L = (size_t)(H / 8) * (W / 8);
-  p->xa = (float*)ar.take(E0 * 4);
-  p->xb = (float*)ar.take(E0 * 4);
+  const size_t Lp0 = (L + 7) / 8 * 8;
+  p->xa = ar.take(E0 * (s16 ? 2 : 4));
+  p->xb = ar.take(E0 * (s16 ? 2 : 4));
   p->oa = ar.take(E0 * osz);
   p->ob = ar.take(E0 * osz);
-  p->x16 = tc ? ar.take(E0 * osz) : nullptr;        // 16-bit copy of x feeding a downsample; V^T in attention
-  p->x16b = tc ? ar.take(E0 / 4 * osz) : nullptr;   // 16-bit copy of a downsample output feeding nin_shortcut
+  // fp32 stream: 16-bit copy of x feeding a downsample (also V^T in attention) and of a downsample output feeding
+  // nin_shortcut.  16-bit stream: x is its own operand copy; only V^T needs room.
+  p->x16 = tc ? ar.take(s16 ? (size_t)Bc * 512 * Lp0 * 2 : E0 * osz) : nullptr;
+  p->x16b = (tc && !s16) ? ar.take(E0 / 4 * osz) : nullptr;
   p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   p->stats2 = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   const size_t Lp = (L + 7) / 8 * 8;                  // row pitch of S / P / V^T (16-byte rows for TMA)
@@ -404,16 +411,35 @@ void make_plan(bool tc, int Bc, int H, int W, Arena& ar, Plan* p) {
 
 struct Fwd {
   SfvEncoder* e; cudaStream_t s; bool tc; int fmt; Plan pl; int N;
+  bool s16 = false;          // residual stream stored as 16-bit * xc_scale
 
   // GroupNorm(32, eps 1e-6)(+SiLU).  `ready`: statistics already accumulated by the producing
   // kernel's epilogue (tensor-core mode); otherwise a statistics pass runs first (check mode).
-  int gn(const NormW& nw, const void* in, bool in_is16, long long HW, int silu, void* out, const double* ready) {
+  int gn(const NormW& nw, const void* in, bool in_is16, long long HW, int silu, void* out, const double* ready,
+         float in_mul = 1.f) {
     if (!ready) {
       SFV_TRY(launch_gn_stats(in, in_is16, fmt, N, HW, nw.C, 32, pl.stats, s));
       ready = pl.stats;
     }
     return launch_gn_apply(in, in_is16, ready, nw.gamma, nw.beta, out, tc, fmt, N, HW, nw.C, 32, 1e-6f, silu, s,
-                           tc && e->range_check);
+                           tc && e->range_check, in_mul);
+  }
+  // GroupNorm of the residual stream x (fp32, or 16-bit scaled by xc_scale)
+  int gn_x(const NormW& nw, const void* x, long long HW, int silu, void* out) {
+    return gn(nw, x, s16, HW, silu, out, sx(), s16 ? 1.f / e->xc_scale : 1.f);
+  }
+  // A convolution that produces the next residual-stream tensor `xo` (+ optional residual `res` from the stream,
+  // + optional 16-bit operand copy for the fp32-stream mode): handles both stream representations.
+  int conv_x(const ConvW& w, const void* in_op, float in_scale, int H, int W, int stride, const void* res, void* xo,
+             void* copy, const void* a2 = nullptr) {
+    const int pad_lo = (w.ks == 3 && stride == 1) ? 1 : 0;
+    const int pad_hi = (w.ks == 3) ? 1 : 0;
+    const float xs = e->xc_scale;
+    if (!tc) return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, (const float*)res, (float*)xo, 0, 1.f, s);
+    if (s16)
+      return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, nullptr, xo, 0, s, sx(), a2, in_scale, xs,
+                     res != nullptr, 1.f / xs);
+    return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, (float*)xo, copy, 0, s, sx(), a2, in_scale, xs);
   }
   // formats of a conv whose A operand is a GroupNorm / conv1 output (fmt) and whose 16-bit output is one too
   TcFmt cf() const { return TcFmt{fmt, e->fmt_w, fmt}; }
@@ -434,38 +460,37 @@ struct Fwd {
   double* sx() { return (tc && e->fused_stats) ? pl.stats2 : nullptr; }
   double* sh() { return (tc && e->fused_stats) ? pl.stats : nullptr; }
 
-  // x: fp32 stream (C=Cin), x_op: operand copy of x (needed only when r.has_nin).
-  // Writes the block output to `xo` (and its operand copy to pl.x16 if want_copy).
-  int resblock(const ResW& r, const float* x, const void* x_op, int H, int W, float* xo, bool want_copy,
+  // x: residual stream (C=Cin), x_op: 16-bit operand copy of x (needed only when r.has_nin; == x with a 16-bit stream).
+  // Writes the block output to `xo` (and, fp32 stream only, its operand copy to pl.x16 if want_copy).
+  int resblock(const ResW& r, const void* x, const void* x_op, int H, int W, void* xo, bool want_copy,
                const void** xo_op) {
     const long long HW = (long long)H * W;
-    SFV_TRY(gn(r.n1, x, false, HW, 1, pl.oa, sx()));
+    SFV_TRY(gn_x(r.n1, x, HW, 1, pl.oa));
     SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
     SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
-    const float* res = x;
-    void* copy = (tc && want_copy) ? pl.x16 : nullptr;
-    const float xs = e->xc_scale;              // the 16-bit copies of x hold xs * x
+    const void* res = x;
+    void* copy = (tc && want_copy && !s16) ? pl.x16 : nullptr;
+    const float xs = e->xc_scale;              // the 16-bit copies of x (or x itself) hold xs * x
     if (r.has_nin && tc && e->fuse_nin) {
       // x' = nin(x) + conv2(a2): one GEMM, the 1x1 shortcut rides along as extra K chunks read from x's 16-bit copy
       // (its weights carry 1 / xs, see get_res)
-      SFV_TRY(conv_tc(r.c2n, cf(), pl.oa, N, H, W, 1, 1, 1, nullptr, xo, copy, 0, s, sx(), x_op, 1.f, xs));
-      *xo_op = copy;
-      return 0;
+      SFV_TRY(conv_x(r.c2n, pl.oa, 1.f, H, W, 1, nullptr, xo, copy, x_op));
+    } else {
+      if (r.has_nin) {
+        SFV_TRY(conv_x(r.nin, x_op, tc ? xs : 1.f, H, W, 1, nullptr, xo, nullptr));
+        res = xo;
+      }
+      SFV_TRY(conv_x(r.c2, pl.oa, 1.f, H, W, 1, res, xo, copy));
     }
-    if (r.has_nin) {
-      SFV_TRY(conv(r.nin, x_op, H, W, 1, nullptr, xo, nullptr, nullptr, tc ? xs : 1.f));
-      res = xo;
-    }
-    SFV_TRY(conv(r.c2, pl.oa, H, W, 1, res, xo, copy, sx(), 1.f, xs));
-    *xo_op = tc ? copy : (const void*)xo;
+    *xo_op = tc ? (s16 ? (const void*)xo : (const void*)copy) : (const void*)xo;
     return 0;
   }
 
-  int attention(const float* x, int h, int w, float* xo) {
+  int attention(const void* x, int h, int w, void* xo) {
     const int L = h * w;
     const int C = 512;
     const float scale = 1.0f / sqrtf((float)C);
-    SFV_TRY(gn(e->attn_norm, x, false, L, 0, pl.oa, sx()));       // hn (no SiLU)
+    SFV_TRY(gn_x(e->attn_norm, x, L, 0, pl.oa));                   // hn (no SiLU)
     if (tc) {
       const int Lp = (L + 7) / 8 * 8;                       // token counts need not be a multiple of 8: padded row pitch
       uint16_t* qk = (uint16_t*)pl.ob;                      // [N][L][1024]: q | k
@@ -481,7 +506,11 @@ struct Fwd {
                              vT + (size_t)n0 * C * Lp, e->v.bias, pl.S, pl.P, O + (size_t)n0 * L * C, nn, L, C,
                              scale, s));
       }
-      SFV_TRY(conv_tc(e->proj, TcFmt{fa, e->fmt_w, fmt}, O, N, h, w, 1, 0, 0, x, xo, nullptr, 0, s, sx()));
+      if (s16)
+        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, nullptr, xo, 0, s, sx(), nullptr, 1.f,
+                        e->xc_scale, 1, 1.f / e->xc_scale));
+      else
+        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, (float*)xo, nullptr, 0, s, sx()));
     } else {
       float* q = (float*)pl.ob;
       float* k = q + (size_t)N * L * C;
@@ -495,7 +524,7 @@ struct Fwd {
         SFV_TRY(attention_f32(q + (size_t)n0 * L * C, k + (size_t)n0 * L * C, v + (size_t)n0 * L * C,
                               O + (size_t)n0 * L * C, pl.S, nn, L, C, scale, s));
       }
-      SFV_TRY(conv_f32(e->proj, O, SRC_NHWC_F32, N, h, w, 1, 0, 0, x, xo, 0, 1.f, s));
+      SFV_TRY(conv_f32(e->proj, O, SRC_NHWC_F32, N, h, w, 1, 0, 0, (const float*)x, (float*)xo, 0, 1.f, s));
     }
     return 0;
   }
@@ -588,7 +617,7 @@ size_t encoder_workspace(const SfvEncoder* e, int B, int H, int W) {
   const int Bc = B < e->chunk ? B : e->chunk;
   Arena ar(nullptr, 0);
   Plan p;
-  make_plan(e->prec != SFV_PREC_F32, Bc, H, W, ar, &p);
+  make_plan(e->prec != SFV_PREC_F32, e->prec != SFV_PREC_F32 && e->stream16, Bc, H, W, ar, &p);
   return ar.off + 1024;
 }
 
@@ -612,11 +641,16 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
   for (int b0 = 0; b0 < B; b0 += chunk) {
     Fwd f; f.e = e; f.s = s; f.tc = tc; f.fmt = e->fmt; f.N = (B - b0) < chunk ? (B - b0) : chunk;
     Arena ar(ws, ws_bytes);
-    make_plan(tc, chunk, H, W, ar, &f.pl);
+    make_plan(tc, tc && e->stream16, chunk, H, W, ar, &f.pl);
+    f.s16 = tc && e->stream16;
     const int N = f.N;
-    auto tap = [&](int idx, const float* src, int hh, int ww) -> int {
+    const bool s16 = f.s16;
+    // taps are fp32 NHWC copies of block outputs (layer-wise parity); a 16-bit stream is widened (and un-scaled)
+    auto tap = [&](int idx, const void* src, int hh, int ww, bool stream = true) -> int {
       if (!taps || !taps[idx]) return 0;
       const size_t per = (size_t)hh * ww * tapC[idx];
+      if (stream && s16)
+        return launch_16_to_f32_scaled(src, taps[idx] + (size_t)b0 * per, (long long)per * N, e->fmt, 1.f / e->xc_scale, s);
       SFV_CUDA(cudaMemcpyAsync(taps[idx] + (size_t)b0 * per, src, per * N * 4, cudaMemcpyDeviceToDevice, s));
       return 0;
     };
@@ -624,12 +658,16 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
     if (f.sx()) SFV_CUDA(cudaMemsetAsync(f.sx(), 0, sizeof(double) * 2 * 32 * N, s));
     if (tc && src_kind == SRC_NHWC_U8 && e->conv_in.w16_u8 && e->conv_in_tc && W % 8 == 0 && ((uintptr_t)xin & 3) == 0)
-      SFV_TRY(conv_in_tc(e->conv_in, e->fmt_w, (const unsigned char*)xin, N, H, W, f.pl.xa, f.sx(), s));
+      SFV_TRY(conv_in_tc(e->conv_in, e->fmt_w, (const unsigned char*)xin, N, H, W, s16 ? nullptr : (float*)f.pl.xa, f.sx(), s,
+                         s16 ? f.pl.xa : nullptr, e->fmt, e->xc_scale));
     else
-      SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, f.pl.xa, f.sx(), N, H, W, s));
+      SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, (float*)f.pl.xa, f.sx(), N, H, W, s,
+                             s16 ? f.pl.xa : nullptr, e->fmt, e->xc_scale));
     SFV_TRY(tap(0, f.pl.xa, H, W));
-    float* cur = f.pl.xa; float* oth = f.pl.xb;
-    const void* cur_op = tc ? nullptr : (const void*)cur;
+    void* cur = f.pl.xa; void* oth = f.pl.xb;
+    // operand view of the stream for convs that read x directly: the stream itself (fp32 check mode, 16-bit stream) or
+    // a 16-bit copy written next to the fp32 stream where one is needed
+    const void* cur_op = (!tc || s16) ? (const void*)cur : nullptr;
     int ch = H, cw = W;
     for (int l = 0; l < 4; ++l) {
       for (int b = 0; b < 2; ++b) {
@@ -641,12 +679,11 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
       }
       if (l != 3) {
         // downsample output feeds down.(l+1).block.0, whose nin_shortcut (levels 1, 2) reads x directly
-        const bool want_copy = tc && e->down[l + 1][0].has_nin;
-        SFV_TRY(f.conv(e->ds[l], cur_op, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr, f.sx(),
-                       tc ? e->xc_scale : 1.f, e->xc_scale));
+        const bool want_copy = tc && !s16 && e->down[l + 1][0].has_nin;
+        SFV_TRY(f.conv_x(e->ds[l], cur_op, tc ? e->xc_scale : 1.f, ch, cw, 2, nullptr, oth, want_copy ? f.pl.x16b : nullptr));
         ch /= 2; cw /= 2;
         std::swap(cur, oth);
-        cur_op = tc ? (want_copy ? (const void*)f.pl.x16b : nullptr) : (const void*)cur;
+        cur_op = (!tc || s16) ? (const void*)cur : (want_copy ? (const void*)f.pl.x16b : nullptr);
         SFV_TRY(tap(9 + l, cur, ch, cw));
       }
     }
@@ -659,9 +696,9 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     SFV_TRY(f.resblock(e->mid2, cur, nullptr, ch, cw, oth, false, &cur_op));
     std::swap(cur, oth);
     SFV_TRY(tap(14, cur, ch, cw));
-    SFV_TRY(f.gn(e->norm_out, cur, false, L, 1, f.pl.oa, f.sx()));
+    SFV_TRY(f.gn_x(e->norm_out, cur, L, 1, f.pl.oa));
     SFV_TRY(f.conv(e->conv_out, f.pl.oa, ch, cw, 1, nullptr, f.pl.moments, nullptr, nullptr));
-    SFV_TRY(tap(15, f.pl.moments, ch, cw));
+    SFV_TRY(tap(15, f.pl.moments, ch, cw, false));
     SFV_TRY(launch_head(f.pl.moments, params + (size_t)b0 * 8 * L, logvar + (size_t)b0 * 4 * L,
                         stdv ? stdv + (size_t)b0 * 4 * L : nullptr, var ? var + (size_t)b0 * 4 * L : nullptr, N,
                         (int)L, s));

@@ -31,11 +31,13 @@ struct TcFmt { int a, b, out; };
 inline TcFmt tcfmt(int f) { return TcFmt{f, f, f}; }
 int make_conv_in_u8(DeviceBlob& blob, const float* w_oihw, int fmt, ConvW* out);
 int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, int W, float* out_f32, double* gn_stats,
-               cudaStream_t s);
+               cudaStream_t s, void* out_16 = nullptr, int fmt_out = 0, float out16_scale = 1.f);
 // in_scale: the A tensor holds in_scale * (true input) (MIXED mode x copies); out16_scale: out_16 = to16(out16_scale * y)
+// residual: fp32, or (res16) a 16-bit tensor in fmt.out added as res_mul * value (the scaled 16-bit residual stream)
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
-            int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats = nullptr, const void* a2_16 = nullptr, float in_scale = 1.f, float out16_scale = 1.f);
+            int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
+            double* gn_stats = nullptr, const void* a2_16 = nullptr, float in_scale = 1.f, float out16_scale = 1.f,
+            int res16 = 0, float res_mul = 1.f);
 inline int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
                    int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
                    double* gn_stats = nullptr, const void* a2_16 = nullptr) {
@@ -65,6 +67,7 @@ struct SfvEncoder {
   int fmt_w = 0, fmt_attn = 0;
   float xc_scale = 1.f;
   bool range_check = false;    // MIXED: fp16 store sites are range-checked on the device
+  bool stream16 = false;       // MIXED: the residual stream x itself is stored as fp16 * xc_scale (no fp32 copy of x in HBM)
   bool fuse_nin = true;        // nin_shortcut folded into conv2's GEMM (tensor-core modes)
   bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
   bool conv_in_tc = true;      // uint8-fed conv_in on the tensor pipe (tensor-core modes; SFV_CONV_IN_TC=0: CUDA cores)

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, void* __restrict__ y,
                                                           int fmt, long long HW, int C, int G, float eps,
-                                                          int do_silu, int pix_per_block, int* err) {
+                                                          int do_silu, int pix_per_block, int* err, float in_mul) {
   __shared__ float sh_mean[64], sh_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / G;
@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
   for (int j = 0; j < 8; ++j) {
     const int c = tc * 8 + j;
     const int g = c / cpg;
-    sc[j] = gamma[c] * sh_rstd[g];
-    sf[j] = beta[c] - sh_mean[g] * sc[j];
+    const float gr = gamma[c] * sh_rstd[g];
+    sc[j] = gr * in_mul;                       // the stored input is (true value) / in_mul (scaled 16-bit stream)
+    sf[j] = beta[c] - sh_mean[g] * gr;
   }
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = min(p0 + (long long)pix_per_block, HW);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, void* __restrict__ y,
                                                                int fmt, long long HW, int C, int G, float eps,
-                                                               int do_silu, int pix_per_block, int* err, int* wd_err) {
+                                                               int do_silu, int pix_per_block, int* err, int* wd_err, float in_mul) {
   extern __shared__ __align__(128) uint8_t ring[];
   __shared__ float sh_mean[64], sh_rstd[64];
   __shared__ __align__(8) uint64_t full[kBulkSlots];
@@ -254,8 +255,9 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
   for (int j = 0; j < 8; ++j) {
     const int c = tc * 8 + j;
     const int g = c / cpg;
-    sc[j] = gamma[c] * sh_rstd[g];
-    sf[j] = beta[c] - sh_mean[g] * sc[j];
+    const float gr = gamma[c] * sh_rstd[g];
+    sc[j] = gr * in_mul;                       // the stored input is (true value) / in_mul (scaled 16-bit stream)
+    sf[j] = beta[c] - sh_mean[g] * gr;
   }
   for (int piece = 0; piece < npieces; ++piece) {
     const int slot = piece % kBulkSlots;
@@ -342,9 +344,9 @@ __global__ void f32_to_16_kernel(const float* x, uint16_t* y, long long n, int f
   }
 }
 
-__global__ void f16_to_32_kernel(const uint16_t* x, float* y, long long n, int fmt) {
+__global__ void f16_to_32_kernel(const uint16_t* x, float* y, long long n, int fmt, float mul) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = f16_to_32(x[i], fmt);
+  if (i < n) y[i] = f16_to_32(x[i], fmt) * mul;
 }
 
 // one block per row; cols up to 16384 (mid-block attention at 1024^2)
@@ -482,7 +484,7 @@ int launch_gn_stats(const void* x, int x_is16, int fmt, int N, long long HW, int
 
 int launch_gn_apply(const void* x, int x_is16, const double* stats, const float* gamma, const float* beta,
                     void* y, int y_is16, int fmt, int N, long long HW, int C, int G, float eps, int silu,
-                    cudaStream_t s, int range_check) {
+                    cudaStream_t s, int range_check, float in_mul) {
   const int cpg = C / G;
   DevState* ds = nullptr;
   SFV_TRY(dev_state(&ds));
@@ -508,17 +510,17 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
         SFV_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSlots * kBulkPieceBytes));
       }
       const size_t sm = kBulkSlots * kBulkPieceBytes;
-      if (x_is16 && y_is16) gn_apply_bulk_kernel<true, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
-      else if (!x_is16 && y_is16) gn_apply_bulk_kernel<false, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
-      else if (x_is16 && !y_is16) gn_apply_bulk_kernel<true, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
-      else gn_apply_bulk_kernel<false, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd);
+      if (x_is16 && y_is16) gn_apply_bulk_kernel<true, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd, in_mul);
+      else if (!x_is16 && y_is16) gn_apply_bulk_kernel<false, true><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd, in_mul);
+      else if (x_is16 && !y_is16) gn_apply_bulk_kernel<true, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd, in_mul);
+      else gn_apply_bulk_kernel<false, false><<<grid, 256, sm, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, wd, in_mul);
       SFV_LAUNCH_OK();
       return 0;
     }
-    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
-    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
-    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
-    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err);
+    if (x_is16 && y_is16) gn_apply_kernel<true, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, in_mul);
+    else if (!x_is16 && y_is16) gn_apply_kernel<false, true><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, in_mul);
+    else if (x_is16 && !y_is16) gn_apply_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, in_mul);
+    else gn_apply_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, gamma, beta, y, fmt, HW, C, G, eps, silu, ppb, err, in_mul);
   } else {
     SFV_CHECK(!x_is16 && !y_is16, "group_norm: scalar path is fp32 only");
     const long long total = (long long)N * HW * C;
@@ -537,10 +539,13 @@ int launch_f32_to_16(const float* x, void* y, long long n, int fmt, cudaStream_t
   return 0;
 }
 
-int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s) {
-  f16_to_32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint16_t*)x, y, n, fmt);
+int launch_16_to_f32_scaled(const void* x, float* y, long long n, int fmt, float mul, cudaStream_t s) {
+  f16_to_32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uint16_t*)x, y, n, fmt, mul);
   SFV_LAUNCH_OK();
   return 0;
+}
+int launch_16_to_f32(const void* x, float* y, long long n, int fmt, cudaStream_t s) {
+  return launch_16_to_f32_scaled(x, y, n, fmt, 1.f, s);
 }
 
 int launch_softmax_rows(const float* x, void* y, int y_is16, int fmt, long long rows, int cols,

@@ -91,7 +91,10 @@ size_t rbvae_workspace(const SfvRbvae* r, int N) {
   Arena ar(nullptr, 0);
   ar.take((size_t)N * h[1] * w[1] * r->channels * 4);
   ar.take((size_t)N * h[2] * w[2] * r->channels * 4);
-  ar.take((size_t)N * r->L * 4 * 2);
+  int KS, splits;
+  fc_plan((long long)h[3] * w[3] * r->channels, r->L, &KS, &splits);
+  ar.take((size_t)splits * N * r->L * 4);       // fc split-K partial sums
+  ar.take((size_t)N * r->L * 4);
   return ar.off + 1024;
 }
 
@@ -108,7 +111,10 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
   Arena ar(ws, ws_bytes);
   float* a1 = (float*)ar.take((size_t)N * h[1] * w[1] * r->channels * 4);
   float* a2 = (float*)ar.take((size_t)N * h[2] * w[2] * r->channels * 4);
-  float* logits = (float*)ar.take((size_t)N * r->L * 4);
+  int KS, splits;
+  const long long Kfc = (long long)h[3] * w[3] * r->channels;
+  fc_plan(Kfc, r->L, &KS, &splits);
+  float* partial = (float*)ar.take((size_t)splits * N * r->L * 4);
   float* hbuf = (float*)ar.take((size_t)N * r->L * 4);
   // frames may exceed the grid.z limit of the GEMM kernel -> slices of 32768
   for (int n0 = 0; n0 < N; n0 += 32768) {
@@ -136,11 +142,11 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
       // third conv output reuses a1 (dead after conv 2)
       SFV_TRY(conv_f32(r->c2, a2i, SRC_NHWC_F32, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, 0, 1.f, s));
     }
-    SFV_TRY(launch_fc(a1i, r->fc_w, r->fc_b, logits + (size_t)n0 * r->L, nn,
-                      (long long)h[3] * w[3] * r->channels, r->L, nullptr, 0, s));
+    SFV_TRY(launch_fc(a1i, r->fc_w, partial + (size_t)n0 * r->L, nn, N, Kfc, r->L, s));
   }
   float* hb = h_out ? h_out : hbuf;
-  return launch_lstm_code(logits, B, T, r->L, r->layers, r->w_ih, r->w_hh, r->lstm_b, u, noise_ratio,
+  // fc partial sums + bias are reduced inside the LSTM kernel's load: fc -> LSTM -> threshold -> pack, no logits tensor
+  return launch_lstm_code(partial, splits, r->fc_b, B, T, r->L, r->layers, r->w_ih, r->w_hh, r->lstm_b, u, noise_ratio,
                           temperature, hard, hb, z_out, codes, s);
 }
 

@@ -7,30 +7,65 @@
 namespace sfv {
 namespace {
 
-// y[n][l] = bias[l] + sum_k x[n][k] * w[l][k].  grid (L, N), block 256.
-__global__ void __launch_bounds__(256) fc_kernel(const float* x, const float* w, const float* bias,
-                                                 float* y, long long K, int L) {
-  __shared__ float red[8];
-  const int l = blockIdx.x, n = blockIdx.y;
-  const float* xr = x + (long long)n * K;
-  const float* wr = w + (long long)l * K;
-  float acc = 0.f;
-  const long long K4 = K & ~3ll;
-  for (long long k = (long long)threadIdx.x * 4; k < K4; k += 1024) {
-    const float4 a = *reinterpret_cast<const float4*>(xr + k);
-    const float4 b = *reinterpret_cast<const float4*>(wr + k);
-    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
-    acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+// ---- fc (percep_RBVAE_model.py:61,67): logits[n][l] = bias[l] + sum_k x[n][k] w[l][k] ------------------------------
+// HBM-bound skinny GEMM (L <= 256 outputs, K up to 262144 inputs per frame): every byte of x and of w is read from
+// HBM exactly once.  Split-K: block s owns the K-slice [s*KS, (s+1)*KS), keeps its slice of the weight in shared
+// memory (transposed to [k][l], so lane = l reads conflict-free and x is a broadcast) and streams the same slice of
+// EVERY frame past it, four frames at a time (register blocking: one 16-byte broadcast load of x feeds four FMAs).
+// It writes partial[s][n][l]; the sum over s (fixed order: deterministic, no atomics) and the bias are folded into
+// the LSTM kernel's load, so the logits never exist as a tensor of their own (fc -> LSTM -> threshold -> pack).
+constexpr int kFcThreads = 256;
+constexpr int kFcFrames = 4;
+constexpr int kFcWFloats = 16384;          // weight slice per block: 64 KB
+
+__global__ void __launch_bounds__(kFcThreads) fc_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               float* __restrict__ partial, int N, long long n_stride,
+                                                               long long K, int L, int Lp, int KS) {
+  extern __shared__ float fsm[];
+  float* wt = fsm;                                   // [KS][Lp]
+  float* xs = fsm + (size_t)KS * Lp;                 // [KS][4]
+  float* red = xs + (size_t)KS * kFcFrames;          // [8 warps][Lp][4]
+  const int s = blockIdx.x;
+  const long long k0 = (long long)s * KS;
+  const int kn = (int)min((long long)KS, K - k0);    // valid k in this slice
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // stage the weight slice, transposed: coalesced reads along k, writes [k][l]
+  for (int i = threadIdx.x; i < Lp * KS; i += kFcThreads) {
+    const int l = i / KS, k = i - l * KS;
+    wt[k * Lp + l] = (l < L && k < kn) ? w[(long long)l * K + k0 + k] : 0.f;
   }
-  for (long long k = K4 + threadIdx.x; k < K; k += 256) acc = fmaf(xr[k], wr[k], acc);
+  const int lchunks = Lp >> 5;
+  const int kw0 = warp * (KS >> 3), kw1 = kw0 + (KS >> 3);     // this warp's k sub-slice
+  for (int n0 = 0; n0 < N; n0 += kFcFrames) {
+    __syncthreads();                                 // previous group's xs / red are consumed (also covers the wt stage)
+    for (int i = threadIdx.x; i < kFcFrames * KS; i += kFcThreads) {
+      const int f = i / KS, k = i - f * KS;
+      const int n = n0 + f;
+      xs[k * kFcFrames + f] = (n < N && k < kn) ? x[(long long)n * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    for (int lc = 0; lc < lchunks; ++lc) {
+      const int l = lc * 32 + lane;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int k = kw0; k < kw1; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + k * kFcFrames);
+        const float wv = wt[k * Lp + l];
+        a0 = fmaf(xv.x, wv, a0); a1 = fmaf(xv.y, wv, a1); a2 = fmaf(xv.z, wv, a2); a3 = fmaf(xv.w, wv, a3);
+      }
+      *reinterpret_cast<float4*>(red + ((size_t)warp * Lp + l) * 4) = make_float4(a0, a1, a2, a3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Lp * kFcFrames; i += kFcThreads) {
+      const int l = i >> 2, f = i & 3;
+      const int n = n0 + f;
+      if (l < L && n < N) {
+        float t = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += red[i];
-    y[(long long)n * L + l] = s + bias[l];
+        for (int wv = 0; wv < 8; ++wv) t += red[((size_t)wv * Lp + l) * 4 + f];
+        partial[((long long)s * n_stride + n) * L + l] = t;
+      }
+    }
   }
 }
 
@@ -40,7 +75,8 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 // Stacked LSTM from zero state, PyTorch gate order (i, f, g, o); layer-major so
 // that layer l consumes the whole output sequence of layer l-1 (in place in hbuf).
 // Then binary_concrete_logits on the top layer's hidden state.
-__global__ void lstm_code_kernel(const float* logits, int T, int L, int layers,
+// `logits`: [n][L] ready values (splits == 0), or the fc layer's split-K partial sums [splits][n_total][L] with `fc_bias`.
+__global__ void lstm_code_kernel(const float* logits, int splits, long long n_total, const float* fc_bias, int T, int L, int layers,
                                  const float* w_ih, const float* w_hh, const float* bias,
                                  const float* u, float noise_ratio, float temperature, int hard,
                                  float* hbuf, float* z_out, uint32_t* codes) {
@@ -53,7 +89,16 @@ __global__ void lstm_code_kernel(const float* logits, int T, int L, int layers,
   const int j = threadIdx.x;
   float* seq = hbuf + (long long)b * T * L;
   for (int t = 0; t < T; ++t)
-    for (int i = j; i < L; i += blockDim.x) seq[t * L + i] = logits[((long long)b * T + t) * L + i];
+    for (int i = j; i < L; i += blockDim.x) {
+      const long long bt = (long long)b * T + t;
+      float v;
+      if (splits == 0) v = logits[bt * L + i];
+      else {
+        v = fc_bias[i];
+        for (int sp = 0; sp < splits; ++sp) v += logits[((long long)sp * n_total + bt) * L + i];   // fixed order
+      }
+      seq[t * L + i] = v;
+    }
   __syncthreads();
   for (int l = 0; l < layers; ++l) {
     const float* Wi = w_ih + (long long)l * 4 * L * L;
@@ -116,23 +161,47 @@ __global__ void hamming_kernel(const uint32_t* a, int Na, const uint32_t* b, int
 
 }  // namespace
 
-int launch_fc(const float* x, const float* w, const float* bias, float* y, int N, long long K, int L,
-              float*, int, cudaStream_t s) {
-  SFV_CHECK(N <= 65535, "fc: N too large");
-  fc_kernel<<<dim3(L, N), 256, 0, s>>>(x, w, bias, y, K, L);
+// split-K geometry of the fc layer for (K, L): slice length KS and number of slices
+void fc_plan(long long K, int L, int* KS, int* splits) {
+  const int Lp = (L + 31) / 32 * 32;
+  int ks = kFcWFloats / Lp;
+  ks = ks / 8 * 8;                              // eight warps split the slice evenly
+  if (ks < 8) ks = 8;
+  if ((long long)ks > K) ks = (int)((K + 7) / 8 * 8);
+  *KS = ks;
+  *splits = (int)((K + ks - 1) / ks);
+}
+
+// partial: [splits][n_stride][L] (fc_plan), rows 0..N-1 of every slice written; the consumer (launch_lstm_code) adds the
+// bias and the slices
+int launch_fc(const float* x, const float* w, float* partial, int N, long long n_stride, long long K, int L, cudaStream_t s) {
+  SFV_CHECK(L >= 1 && L <= 256, "fc: latent_dim %d out of range [1,256]", L);
+  int KS, splits;
+  fc_plan(K, L, &KS, &splits);
+  const int Lp = (L + 31) / 32 * 32;
+  const size_t smem = ((size_t)KS * Lp + (size_t)KS * kFcFrames + (size_t)8 * Lp * 4) * sizeof(float);
+  static unsigned long long attr_devs = 0;
+  int dev = 0;
+  SFV_CUDA(cudaGetDevice(&dev));
+  if (first_use_on_device(attr_devs, dev))
+    SFV_CUDA(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  SFV_CHECK(smem <= 100 * 1024, "fc: shared-memory plan too large (%zu)", smem);
+  ProfScope prof(PROF_OTHER, ((double)N * K + (double)L * K) * 4.0, s);
+  fc_splitk_kernel<<<splits, kFcThreads, smem, s>>>(x, w, partial, N, n_stride, K, L, Lp, KS);
   SFV_LAUNCH_OK();
   return 0;
 }
 
-int launch_lstm_code(const float* logits, int B, int T, int L, int layers, const float* w_ih,
+int launch_lstm_code(const float* logits, int splits, const float* fc_bias, int B, int T, int L, int layers, const float* w_ih,
                      const float* w_hh, const float* bias, const float* u, float noise_ratio,
                      float temperature, int hard, float* h_out, float* z_out, uint32_t* codes,
                      cudaStream_t s) {
+  SFV_CHECK(splits == 0 || fc_bias != nullptr, "lstm: split-K partials need the fc bias");
   SFV_CHECK(L >= 1 && L <= 256, "lstm: latent_dim %d out of range [1,256]", L);
   SFV_CHECK(h_out != nullptr, "lstm: h buffer required");
   const int Lpad = (L + 31) / 32 * 32;
   const int threads = 4 * Lpad;
-  lstm_code_kernel<<<B, threads, 7 * L * sizeof(float), s>>>(logits, T, L, layers, w_ih, w_hh, bias, u,
+  lstm_code_kernel<<<B, threads, 7 * L * sizeof(float), s>>>(logits, splits, (long long)B * T, fc_bias, T, L, layers, w_ih, w_hh, bias, u,
                                                              noise_ratio, temperature, hard, h_out, z_out,
                                                              codes);
   SFV_LAUNCH_OK();

@@ -67,7 +67,9 @@ struct TcParams {
   int Wo, Ho, Cout, n_img;
   float alpha;
   const float* bias;
-  const float* residual;
+  const float* residual;               // fp32 residual, or (res16) a 16-bit tensor holding res_scale^-1 ... see res16
+  int res16; float res_mul;            // res16: the residual is 16-bit (format fmt_out) and is added as res_mul * value
+  int res_slot;                        // bytes of one residual / fp32 staging slot: 4096 (fp32 tile) or 2048 (16-bit residual)
   float* out_f32;
   void* out_16;
   int fmt_a, fmt_b, fmt_out;           // 16-bit formats of the A operand, the B operand and out_16
@@ -517,17 +519,17 @@ struct Cfg {
   // (0 or 2) per epilogue warp, see smem_plan().
   static constexpr int kMaxStages = 8;
   static constexpr int kSmemLimit = 232448;
-  static __host__ __device__ constexpr int epi_bytes(int res_bufs, int h16_slots) {
-    return BLOCK_N >= 32 ? kEpiWarps * (res_bufs * 4096 + h16_slots * 2048) : 0;
+  static __host__ __device__ constexpr int epi_bytes(int res_bufs, int h16_slots, int res_slot = 4096) {
+    return BLOCK_N >= 32 ? kEpiWarps * (res_bufs * res_slot + h16_slots * 2048) : 0;
   }
-  static __host__ constexpr int stages_for(int res_bufs, int h16_slots) {
-    const int n = (kSmemLimit - 1024 - kAuxBytes - epi_bytes(res_bufs, h16_slots)) / kStageBytes;
+  static __host__ constexpr int stages_for(int res_bufs, int h16_slots, int res_slot = 4096) {
+    const int n = (kSmemLimit - 1024 - kAuxBytes - epi_bytes(res_bufs, h16_slots, res_slot)) / kStageBytes;
     return n > kMaxStages ? kMaxStages : n;
   }
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
-  static __host__ constexpr int smem_bytes(int stages, int res_bufs, int h16_slots) {
-    return stages * kStageBytes + epi_bytes(res_bufs, h16_slots) + kAuxBytes + 1024 /*align slack*/;
+  static __host__ constexpr int smem_bytes(int stages, int res_bufs, int h16_slots, int res_slot = 4096) {
+    return stages * kStageBytes + epi_bytes(res_bufs, h16_slots, res_slot) + kAuxBytes + 1024 /*align slack*/;
   }
 };
 
@@ -555,8 +557,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_stages = p.num_stages;
   const int kResBufs = p.res_bufs;                                        // fp32 staging slots per epilogue warp (runtime)
   uint8_t* epi_f32 = smem + num_stages * C::kStageBytes;                  // 1024-aligned (stage sizes are)
-  uint8_t* epi_h16 = epi_f32 + C::kEpiWarps * kResBufs * 4096;
-  uint64_t* bars = (uint64_t*)(smem + num_stages * C::kStageBytes + C::epi_bytes(kResBufs, p.h16_slots));
+  const int kResSlot = p.res_slot;                                        // 4096, or 2048 when the residual is 16-bit
+  uint8_t* epi_h16 = epi_f32 + C::kEpiWarps * kResBufs * kResSlot;
+  uint64_t* bars = (uint64_t*)(smem + num_stages * C::kStageBytes + C::epi_bytes(kResBufs, p.h16_slots, kResSlot));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kMaxStages;
   uint64_t* tfull_bar = bars + 2 * C::kMaxStages;
@@ -849,7 +852,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool use_tma = C::kChunk == 32 && p.epi_mode == 1;
     const bool has_res = p.residual != nullptr;
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
-    uint8_t* f32_w = epi_f32 + ew * (kResBufs * 4096);
+    uint8_t* f32_w = epi_f32 + ew * (kResBufs * kResSlot);
     const uint32_t f32_s = smem_u32(f32_w), bias_s = smem_u32(bias_w);
     uint8_t* h16_w = epi_h16 + ew * (p.h16_slots * 2048);
     const uint32_t h16_s = smem_u32(h16_w);
@@ -872,8 +875,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool pf_ok = p.res_prefetch && unit_pf < p.n_units && tp.m_tile < p.n_tiles_m;
       if (elect_one_sync()) {
         const uint32_t bar = smem_u32(&res_bar_w[slot]);
-        mbar_arrive_expect_tx(bar, 4096);
-        tma_load_4d(smem_u32(f32_w + slot * 4096), &tmR, bar, col0, tx * p.BW + wx, ty * p.BH + wy, img);
+        mbar_arrive_expect_tx(bar, (uint32_t)kResSlot);
+        tma_load_4d(smem_u32(f32_w + slot * kResSlot), &tmR, bar, col0, tx * p.BW + wx, ty * p.BH + wy, img);
         if (pf_ok)
           tma_prefetch_4d(&tmR, tp.n_tile * BLOCK_N + cbase + c * 32, tp.tx * p.BW + wx, tp.ty * p.BH + wy, tp.img);
       }
@@ -1003,7 +1006,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld32(t_row + cbase + c0, v);
             const int slot = kResBufs ? rslot : 0;
-            const uint32_t fb = f32_s + slot * 4096 + lane * 128;
+            const uint32_t fb = f32_s + slot * kResSlot + lane * 128;     // fp32 tile row (only meaningful with 4096-byte slots)
             const uint32_t bw = bias_s + c0 * 4;
             float f[32];
             unsigned long long tq = kFineDbg && p.dbg ? clock64() : 0;
@@ -1012,6 +1015,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (!ok) break;
               if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[0] += t1 - tq; tq = t1; }
               tmem_ld_wait();
+              if (p.res16) {
+                // 16-bit residual stream (MIXED: fp16 x 2^-6): 32 rows x 64 B, 64B-swizzled; value = res_mul * stored
+                const uint32_t rb = f32_s + slot * kResSlot + lane * 64;
+                const float rm = p.res_mul;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 q = lds128(rb + ((j ^ sw16) << 4));
+                  float r8[8];
+                  unpack2_16(__float_as_uint(q.x), p.fmt_out, r8[0], r8[1]); unpack2_16(__float_as_uint(q.y), p.fmt_out, r8[2], r8[3]);
+                  unpack2_16(__float_as_uint(q.z), p.fmt_out, r8[4], r8[5]); unpack2_16(__float_as_uint(q.w), p.fmt_out, r8[6], r8[7]);
+                  const float4 b0 = lds128(bw + j * 32), b1 = lds128(bw + j * 32 + 16);
+                  f[8 * j] = fmaf(r8[0], rm, fmaf(__uint_as_float(v[8 * j]), p.alpha, b0.x));
+                  f[8 * j + 1] = fmaf(r8[1], rm, fmaf(__uint_as_float(v[8 * j + 1]), p.alpha, b0.y));
+                  f[8 * j + 2] = fmaf(r8[2], rm, fmaf(__uint_as_float(v[8 * j + 2]), p.alpha, b0.z));
+                  f[8 * j + 3] = fmaf(r8[3], rm, fmaf(__uint_as_float(v[8 * j + 3]), p.alpha, b0.w));
+                  f[8 * j + 4] = fmaf(r8[4], rm, fmaf(__uint_as_float(v[8 * j + 4]), p.alpha, b1.x));
+                  f[8 * j + 5] = fmaf(r8[5], rm, fmaf(__uint_as_float(v[8 * j + 5]), p.alpha, b1.y));
+                  f[8 * j + 6] = fmaf(r8[6], rm, fmaf(__uint_as_float(v[8 * j + 6]), p.alpha, b1.z));
+                  f[8 * j + 7] = fmaf(r8[7], rm, fmaf(__uint_as_float(v[8 * j + 7]), p.alpha, b1.w));
+                }
+              } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 r4 = lds128(fb + ((j ^ sw) << 4));
@@ -1020,6 +1044,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b4.y) + r4.y;
                 f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b4.z) + r4.z;
                 f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b4.w) + r4.w;
+              }
               }
             } else {
               tmem_ld_wait();
@@ -1079,7 +1104,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
               if (elect_one_sync()) {
                 const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
-                if (p.out_f32) tma_store_4d(&tmO32, f32_s + slot * 4096, col0, ox, oy, img);
+                if (p.out_f32) tma_store_4d(&tmO32, f32_s + slot * kResSlot, col0, ox, oy, img);
                 if (p.out_16) tma_store_4d(&tmO16, h16_s + hslot * 2048, col0, ox, oy, img);
                 tma_store_commit();
                 if (deep_rings) tma_store_wait_read<1>();       // the previous chunk's staging tiles are free again
@@ -1114,7 +1139,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 if (col0 + j < p.Cout) {
-                  if (p.residual) {
+                  if (p.residual && p.res16) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.residual) + row_off + col0 + j);
+                    float r0, r1, r2, r3;
+                    unpack2_16(u.x, p.fmt_out, r0, r1); unpack2_16(u.y, p.fmt_out, r2, r3);
+                    f[j] = fmaf(r0, p.res_mul, f[j]); f[j + 1] = fmaf(r1, p.res_mul, f[j + 1]);
+                    f[j + 2] = fmaf(r2, p.res_mul, f[j + 2]); f[j + 3] = fmaf(r3, p.res_mul, f[j + 3]);
+                  } else if (p.residual) {
                     const float4 b = *reinterpret_cast<const float4*>(p.residual + row_off + col0 + j);
                     f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
                   }
@@ -1288,25 +1319,25 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     const long long chunk_budget = k_chunks_total * (BLOCK_N * kBlockM * kBlockK / 4096) / chunks_per_warp;
     const int floor_stages = HALO ? 2 : 3;
     const bool have_slack = chunk_budget >= (p.residual ? 4000 : 2000);
-    if (g_epi_slots_auto && (C::stages_for(p.res_bufs, p.h16_slots) < floor_stages ||
-                             (C::stages_for(p.res_bufs, p.h16_slots) < want && have_slack))) {
-      const int need = C::stages_for(p.res_bufs, p.h16_slots) < floor_stages && !have_slack ? floor_stages : want;
+    if (g_epi_slots_auto && (C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < floor_stages ||
+                             (C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < want && have_slack))) {
+      const int need = C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < floor_stages && !have_slack ? floor_stages : want;
       const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
       int best_r = p.res_bufs, best_h = p.h16_slots;
       for (int i = 0; i < 4; ++i) {
         const int r = need_f32 ? cand[i][0] : 0, h = need_h16 ? cand[i][1] : 0;
         if (r > p.res_bufs || h > p.h16_slots) continue;
         best_r = r; best_h = h;                                  // candidates get shallower: the last one has the most stages
-        if (C::stages_for(r, h) >= need) break;
+        if (C::stages_for(r, h, p.res_slot) >= need) break;
       }
       p.res_bufs = best_r; p.h16_slots = best_h;
     }
     if (g_epi_slots_r >= 0 && need_f32) p.res_bufs = g_epi_slots_r;       // SFV_EPI_SLOTS=r,h experiment override
     if (g_epi_slots_h >= 0 && need_h16) p.h16_slots = g_epi_slots_h;
   }
-  p.num_stages = C::stages_for(p.res_bufs, p.h16_slots);
+  p.num_stages = C::stages_for(p.res_bufs, p.h16_slots, p.res_slot);
   SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
-  const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots);
+  const int smem_bytes = C::smem_bytes(p.num_stages, p.res_bufs, p.h16_slots, p.res_slot);
   const int max_units = ds.num_sms / NCTA;
   const int n_sched = p.softmax_mode ? p.n_groups : p.n_units;      // schedulable items: tiles, or whole m-tile groups
   const int grid = (n_sched < max_units ? n_sched : max_units) * NCTA;
@@ -1360,6 +1391,9 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   SFV_TRY(dev_state(&dsp));
   const DevState& ds = *dsp;
   const int fmt_b = a.fmt_split ? a.fmt_b : a.fmt, fmt_out = a.fmt_split ? a.fmt_out : a.fmt;
+  // measured on B200: an instruction descriptor with a_format != b_format under kind::f16 raises an illegal-instruction
+  // fault, so the two operands always share a format; only the 16-bit OUTPUT format is free
+  SFV_CHECK(fmt_b == a.fmt, "tc_gemm: A and B operands must share one 16-bit format (got %d / %d)", a.fmt, fmt_b);
   SFV_CHECK(a.BW * a.BH == kBlockM && (a.BW & (a.BW - 1)) == 0, "tc_gemm: bad tile %dx%d", a.BW, a.BH);
   SFV_CHECK(a.ntaps >= 1 && a.ntaps <= 9 && a.kchunks >= 1, "tc_gemm: bad taps/kchunks");
 
@@ -1442,7 +1476,11 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.a2_kchunks = a.a2 ? a.a2_cin / 64 : 0; p.a2_k0 = a.a2_k0;
   p.halo_base_offset = g_halo_boff;
   p.Wo = a.Wo; p.Ho = a.Ho; p.Cout = a.Cout; p.n_img = a.Nimg;
-  p.alpha = a.alpha; p.bias = a.bias; p.residual = a.residual;
+  p.alpha = a.alpha; p.bias = a.bias; p.residual = (const float*)a.residual;
+  p.res16 = a.residual ? a.res16 : 0; p.res_mul = a.res_mul == 0.f ? 1.f : a.res_mul;
+  p.res_slot = p.res16 ? 2048 : 4096;
+  SFV_CHECK(!p.res16 || !a.out_f32, "tc_gemm: a 16-bit residual goes with a 16-bit output only");
+  SFV_CHECK(!p.res16 || a.block_n >= 32, "tc_gemm: 16-bit residual needs block_n >= 32");
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.ldo = a.ldo; p.relu = a.relu;
   p.fmt_a = a.fmt; p.fmt_b = fmt_b; p.fmt_out = fmt_out;
   p.out16_scale = a.out16_scale == 0.f ? 1.f : a.out16_scale;
@@ -1467,7 +1505,8 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     cuuint32_t box[4] = {32, bx, by, 1};
     cuuint64_t st32[4] = {4, (cuuint64_t)a.ldo * 4, (cuuint64_t)a.ldo * 4 * a.Wo, (cuuint64_t)a.ldo * 4 * a.Wo * a.Ho};
     cuuint64_t st16[4] = {2, (cuuint64_t)a.ldo * 2, (cuuint64_t)a.ldo * 2 * a.Wo, (cuuint64_t)a.ldo * 2 * a.Wo * a.Ho};
-    if (a.residual) SFV_TRY(encode_map(&mr, a.fmt, 4, a.residual, dims, st32, box, 128, true));
+    if (a.residual && a.res16) SFV_TRY(encode_map(&mr, fmt_out, 4, a.residual, dims, st16, box, 64, false));
+    else if (a.residual) SFV_TRY(encode_map(&mr, a.fmt, 4, a.residual, dims, st32, box, 128, true));
     if (a.out_f32) SFV_TRY(encode_map(&mo32, a.fmt, 4, a.out_f32, dims, st32, box, 128, true));
     if (a.out_16) SFV_TRY(encode_map(&mo16, fmt_out, 4, a.out_16, dims, st16, box, 64, false));
   }
