@@ -38,7 +38,11 @@ if ROOT not in sys.path:
 
 R, BATCH, LATENT_DIM = 512, 64, 25
 N_INPUT_BUFFERS = 4          # 4 x 50 MB of distinct frames > 126 MB L2: inputs never L2-resident across steps
-RB_GAINS = dict(fc_gain=100.0, bias_gain=0.002, ih_gain=8.0)   # codes follow the frame (weights.make_rbvae_responsive)
+# codes follow the frame (weights.make_rbvae_responsive).  Picked with tools/rb_gain_probe.py on the GPU box: 9 distinct codes
+# over the 16 parity frames, 3 bits inside the |h| < 1e-3 band, and the mixed-mode h within 1.0e-3 of the oracle's -- a
+# steeper recipe (100, 0.002, 8: 14 distinct codes) amplifies the 2.4e-3 latent error to 4e-3 in h, which makes flips
+# OUTSIDE the band a coin toss and says nothing about the kernels
+RB_GAINS = dict(fc_gain=1000.0, bias_gain=0.002, ih_gain=4.0)
 PARITY_FRAMES = 16
 DTYPE_NAMES = {"mixed": "mixed fp16/bf16 operands, fp32 accumulate", "bf16": "bf16", "fp16": "fp16", "fp32": "f32"}
 OPERAND_FORMATS = {

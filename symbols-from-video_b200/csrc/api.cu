@@ -204,10 +204,10 @@ int sfv_rbvae_create_ex(const SfvTensor* tensors, int32_t n_tensors, int32_t in_
   if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
   r->in_channels = in_channels; r->in_h = in_h; r->in_w = in_w;
   if (cudaGetDevice(&r->device) != cudaSuccess) { delete r; return fail(SFV_ERR_CUDA, "cudaGetDevice failed"); }
-  // MIXED: fp16 weights (scaled per layer) with bf16 activations -- the RBVAE's conv inputs are ReLU'd conv outputs,
-  // i.e. not bounded by construction, so they take the range-safe format
-  r->prec = precision; r->fmt = fmt_of_precision(precision);
-  r->fmt_act = precision == SFV_PREC_MIXED ? FMT_BF16 : r->fmt;
+  // MIXED: the RBVAE's conv inputs are ReLU'd conv outputs, i.e. not bounded by construction, so both operands of its
+  // two tensor-core convs take the range-safe format (a tcgen05 GEMM has one operand format)
+  r->prec = precision; r->fmt = precision == SFV_PREC_MIXED ? FMT_BF16 : fmt_of_precision(precision);
+  r->fmt_act = r->fmt;
   int st = rbvae_build(r, tensors, n_tensors);
   if (st != 0) { r->blob.release(); delete r; return st; }
   *out = r;

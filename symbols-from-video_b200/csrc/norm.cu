@@ -74,6 +74,16 @@ __global__ void gn_stats_scalar_kernel(const float* x, long long HW, int C, int 
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
+// SiLU for 16-bit outputs: t * sigmoid(t) = h + h * tanh(h), h = t / 2 -- ONE MUFU op (tanh.approx.f32, relative
+// error 2^-11, i.e. the output format's own rounding step) instead of ex2 + rcp.  The apply pass moves 4 bytes per
+// element with 16-bit input and output, which puts two MUFU ops per element (16 lanes/clk/SM) level with HBM time.
+__device__ __forceinline__ float silu_tanh(float t) {
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
 // fp16 range check on packed pairs: bit 15 of a half of the result is set iff that half's magnitude bits are
 // >= 0x7BFF (65504 = the value a saturating conversion produces, inf, NaN).  OR-accumulated per thread.
 __device__ __forceinline__ uint32_t f16_sat_bits(uint32_t w) { return (w & 0x7FFF7FFFu) + 0x04010401u; }
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const void* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(v[j], sc[j], sf[j]);
-        v[j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
+        v[j] = do_silu ? (OUT16 ? silu_tanh(t) : __fdividef(t, 1.f + __expf(-t))) : t;
       }
       const long long idx = base + pp * C;
       if (OUT16) {
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(v[j], sc[j], sf[j]);
-        v[j] = do_silu ? __fdividef(t, 1.f + __expf(-t)) : t;
+        v[j] = do_silu ? (OUT16 ? silu_tanh(t) : __fdividef(t, 1.f + __expf(-t))) : t;
       }
       const long long idx = ((long long)n * HW + p0 + pp0 + r) * C + tc * 8;
       if (OUT16) {
@@ -490,7 +500,9 @@ int launch_gn_apply(const void* x, int x_is16, const double* stats, const float*
   SFV_TRY(dev_state(&ds));
   int* err = range_check ? ds->err_flag : nullptr;
   int* wd = ds->err_flag;
-  ProfScope prof(PROF_GN_APPLY, (double)N * HW * C * ((x_is16 ? 2 : 4) + (y_is16 ? 2 : 4)), s);
+  char tag[64];
+  snprintf(tag, sizeof(tag), "gn N=%d HW=%lld C=%d in%d out%d", N, HW, C, x_is16 ? 16 : 32, y_is16 ? 16 : 32);
+  ProfScope prof(PROF_GN_APPLY, (double)N * HW * C * ((x_is16 ? 2 : 4) + (y_is16 ? 2 : 4)), s, tag);
   if (C % 8 == 0 && 256 % (C / 8) == 0 && C <= 2048 && G <= 64 && C % G == 0) {
     // slabs sized so that the grid is a few waves of 148 SMs x 8 resident blocks
     long long want = (HW * N + 148 * 16 - 1) / (148 * 16);

@@ -74,6 +74,10 @@ struct TcParams {
   void* out_16;
   int fmt_a, fmt_b, fmt_out;           // 16-bit formats of the A operand, the B operand and out_16
   float out16_scale;                   // out_16 = to16(out16_scale * value); != 1 also range-checks fp16 stores
+  // scaled-domain epilogue (16-bit residual stream): alpha, the bias copy and the residual multiplier already carry the
+  // stream scale s, so the finished value IS the stored value (no per-element multiply); GroupNorm partial sums are
+  // un-scaled when flushed (stat_mul = 1/s for sums, its square for sums of squares; exact, s is a power of two)
+  float bias_mul, stat_mul; int sat_check;
   long long ldo;
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
@@ -440,6 +444,10 @@ __device__ __forceinline__ void epi_stats_chunk(const float* f, bool valid, int 
 // (latency-bound instruction stream), so BLOCK_N = 128 kernels run TWO warps per TMEM lane quarter, each
 // taking half of the columns (kSets = 2, 8 epilogue warps, 2-slot rings); wider tiles keep 4 warps.
 constexpr int kAuxBytes = 512 /*barriers*/ + 2048 /*GN partials*/ + 4096 /*bias copies*/;
+// residual ring depth per epilogue warp: the load of chunk g + depth - 1 is issued while chunk g is processed.  A
+// 16-bit residual tile is 2 KB, so four slots (three chunks of lookahead, ~7000 cycles at level 0) cost what two
+// fp32 slots did; with one chunk of lookahead the epilogue sat on the TMA latency and the MMA warp on tmem_empty.
+constexpr int kMaxResBufs = 4;          // 20 pipeline barriers + 8 warps x 4 + TMEM pointer fit the 512-byte barrier block
 
 // HALO: for 3x3 stride-1 convolutions tiled as 128-pixel row segments, one TMA box of 130 pixels feeds the
 // three horizontal taps of a filter row; the MMAs read it at start addresses shifted by one pixel
@@ -564,8 +572,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + C::kMaxStages;
   uint64_t* tfull_bar = bars + 2 * C::kMaxStages;
   uint64_t* tempty_bar = bars + 2 * C::kMaxStages + 2;
-  uint64_t* res_bar = bars + 2 * C::kMaxStages + 4;                        // [epilogue warps][3]
-  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * 3);
+  uint64_t* res_bar = bars + 2 * C::kMaxStages + 4;                        // [epilogue warps][kMaxResBufs]
+  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * kMaxResBufs);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
   float* gn_acc = (float*)((uint8_t*)bars + 512);        // [epilogue warps][512 / warps floats]: (sum, sumsq) per group
   float* bias_all = gn_acc + 512;                        // [epilogue warps][1024 / warps floats]
@@ -582,7 +590,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&tfull_bar[i]), 1);
       mbar_init(smem_u32(&tempty_bar[i]), C::kEpiWarps * NCTA);
     }
-    for (int i = 0; i < C::kEpiWarps * 3; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    for (int i = 0; i < C::kEpiWarps * kMaxResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     *abort_flag = 0;
     fence_barrier_init();
   }
@@ -812,7 +820,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_w[t] = 0.f;
         const int grp = g0 + (t >> 1);
         if (grp < p.gn_groups)
-          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (t & 1)], (double)val);
+          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (t & 1)],
+                    (double)val * (double)((t & 1) ? p.stat_mul * p.stat_mul : p.stat_mul));
       }
       __syncwarp();
     };
@@ -828,7 +837,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float r = halving_reduce<32>(gacc, lane, idx);
         const int grp = (gn_nt * BLOCK_N + cbase) / 4 + (idx >> 1);
         if (grp < p.gn_groups)
-          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (idx & 1)], (double)r);
+          atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (idx & 1)],
+                    (double)r * (double)((idx & 1) ? p.stat_mul * p.stat_mul : p.stat_mul));
 #pragma unroll
         for (int i = 0; i < 32; ++i) gacc[i] = 0.f;
       }
@@ -839,7 +849,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       for (int j = lane; j < kColsPerSet; j += 32) {
         const int c = n_tile * BLOCK_N + cbase + j;
-        bias_w[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+        bias_w[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) * p.bias_mul : 0.f;
       }
       bias_nt = n_tile;
       __syncwarp();
@@ -859,7 +869,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // a staging slot is rewritten (by the next chunk's math or the next residual load) one chunk after the bulk
     // store that reads it was committed, unless its ring has a single slot: then wait for that store right away
     const bool deep_rings = (kResBufs == 0 || kResBufs >= 2) && (p.h16_slots == 0 || p.h16_slots >= 2);
-    uint64_t* res_bar_w = res_bar + ew * 3;
+    uint64_t* res_bar_w = res_bar + ew * kMaxResBufs;
     auto issue_residual = [&](int g, int slot) {      // whole warp calls; one elected lane issues; slot == g % kResBufs
       const int seq = g / kNChunk, c = g - seq * kNChunk;
       const int unit = unit0 + seq * unit_step;
@@ -1078,10 +1088,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t hb = h16_s + hslot * 2048 + lane * 64;
               if (p.out_16) {
                 if (p.out16_scale == 1.f) {
+                  uint32_t sat = 0;
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    sts128u(hb + ((j ^ sw16) << 4), pack2_16(f[8 * j], f[8 * j + 1], p.fmt_out), pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt_out),
-                            pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt_out), pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt_out));
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t w0 = pack2_16(f[8 * j], f[8 * j + 1], p.fmt_out), w1 = pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt_out);
+                    const uint32_t w2 = pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt_out), w3 = pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt_out);
+                    // fp16 range check of the stored residual stream: a half at the saturation value (or inf / NaN) sets bit 15
+                    if (p.sat_check) sat |= ((w0 & 0x7FFF7FFFu) + 0x04010401u) | ((w1 & 0x7FFF7FFFu) + 0x04010401u) |
+                                            ((w2 & 0x7FFF7FFFu) + 0x04010401u) | ((w3 & 0x7FFF7FFFu) + 0x04010401u);
+                    sts128u(hb + ((j ^ sw16) << 4), w0, w1, w2, w3);
+                  }
+                  if (p.sat_check && row_ok && (sat & 0x80008000u)) atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
                 } else {
                   // scaled 16-bit copy of the residual stream (MIXED mode: fp16 x 2^-6); a value beyond the fp16
                   // range must not saturate silently -> error word (only the few launches that write such copies)
@@ -1311,7 +1328,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   // 512->512 conv2 at 128x128, but 513 -> 551 us on the 256->256 one, hence the threshold).
   p.h16_slots = need_h16 ? 2 : 0;
   // eight epilogue warps hold half as many chunks each: two-slot rings suffice when staging is scarce
-  p.res_bufs = !need_f32 ? 0 : ((C::kSets == 2 && (need_h16 || BLOCK_N == 256)) ? 2 : 3);
+  p.res_bufs = !need_f32 ? 0 : (p.res16 ? kMaxResBufs : ((C::kSets == 2 && (need_h16 || BLOCK_N == 256)) ? 2 : 3));
   {
     const int want = HALO ? 3 : 6;      // non-HALO stages hold one k-chunk (24-32 KB): six of them cover the load latency
     const long long k_chunks_total = (long long)p.ntaps * p.kchunks + p.a2_kchunks;
@@ -1322,9 +1339,9 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     if (g_epi_slots_auto && (C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < floor_stages ||
                              (C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < want && have_slack))) {
       const int need = C::stages_for(p.res_bufs, p.h16_slots, p.res_slot) < floor_stages && !have_slack ? floor_stages : want;
-      const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+      const int cand[6][2] = {{3, 2}, {3, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
       int best_r = p.res_bufs, best_h = p.h16_slots;
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 6; ++i) {
         const int r = need_f32 ? cand[i][0] : 0, h = need_h16 ? cand[i][1] : 0;
         if (r > p.res_bufs || h > p.h16_slots) continue;
         best_r = r; best_h = h;                                  // candidates get shallower: the last one has the most stages
@@ -1484,7 +1501,16 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   p.out_f32 = a.out_f32; p.out_16 = a.out_16; p.ldo = a.ldo; p.relu = a.relu;
   p.fmt_a = a.fmt; p.fmt_b = fmt_b; p.fmt_out = fmt_out;
   p.out16_scale = a.out16_scale == 0.f ? 1.f : a.out16_scale;
+  p.bias_mul = 1.f; p.stat_mul = 1.f; p.sat_check = 0;
   SFV_CHECK(p.out16_scale == 1.f || !a.softmax_mode, "tc_gemm: softmax mode has no scaled 16-bit output");
+  if (p.out16_scale != 1.f && a.out_16 && !a.out_f32 && a.block_n >= 32) {
+    // the only output is the scaled 16-bit tensor: run the whole epilogue in the scaled domain
+    const float sc = p.out16_scale;
+    p.alpha *= sc; p.bias_mul = sc; p.res_mul *= sc; p.stat_mul = 1.f / sc;
+    p.sat_check = fmt_out == FMT_F16;
+    p.out16_scale = 1.f;
+  }
+
   p.gn_stats = a.gn_stats; p.gn_cpg = a.gn_cpg; p.gn_groups = a.gn_cpg ? a.Cout / a.gn_cpg : 0;
   if (a.gn_stats)
     SFV_CHECK((a.gn_cpg == 4 || a.gn_cpg == 8 || a.gn_cpg == 16) && a.Cout % 32 == 0 && a.block_n >= 32 &&
@@ -1547,8 +1573,8 @@ int tc_check_device_error(cudaStream_t s) {
   if (h != 0) {
     cudaMemsetAsync(flag, 0, sizeof(int), s);
     if (h >= kErrRangeBase) {
-      static const char* site[] = {"?", "a GroupNorm(+SiLU) output", "a conv1 output (norm2 input)",
-                                   "a 16-bit copy of the residual stream (Downsample / nin_shortcut input)"};
+      static const char* site[] = {"?", "a GroupNorm(+SiLU) output", "a GroupNorm input (conv1 output / 16-bit residual stream)",
+                                   "a 16-bit store of the residual stream"};
       const int k = h - kErrRangeBase;
       return fail(SFV_ERR_RANGE, "fp16 operand range exceeded at %s: the results of this call are invalid; "
                                  "re-create the encoder with precision bf16", site[(k >= 1 && k <= 3) ? k : 0]);

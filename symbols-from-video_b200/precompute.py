@@ -104,6 +104,7 @@ def precompute_embeddings(source, vae, rbvae=None, target_size=(1280, 720), batc
         return os.path.join(part_dir, f"part-{a:010d}-{b:010d}.npz")
 
     Hs, Ws = source.frame_hw
+    dummy_u = torch.zeros(batch, max(L, 1), device=dev)
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     t_start = time.perf_counter()
@@ -159,7 +160,9 @@ def precompute_embeddings(source, vae, rbvae=None, target_size=(1280, 720), batc
                 r0 = base + first - lo
                 lat = _scaled_sample(post, nz, scale_factor, out=lat_g[r0:r0 + n])
                 if rbvae is not None:
-                    rbvae.encode_codes(lat.unsqueeze(1), temperature=rbvae_temperature, noise_ratio=0.0,
+                    # U given (unused at noise_ratio 0) so the call draws nothing from the global RNG: the only
+                    # consumer of the generator in this loop is the posterior noise, as in the reference's loop
+                    rbvae.encode_codes(lat.unsqueeze(1), temperature=rbvae_temperature, noise_ratio=0.0, U=dummy_u[:n],
                                        out_codes=codes_g[r0:r0 + n], out_h=h_g[r0:r0 + n].view(n, 1, L))
                 e1.record(main)
                 ev_pairs.append((e0, e1))

@@ -86,7 +86,8 @@ def main():
     ap.add_argument("--timeout", type=int, default=180)
     ap.add_argument("--group", type=int, default=12, help="checks per subprocess")
     a = ap.parse_args()
-    items = [it for it in plan() if a.only in it[0]]
+    only = [t for t in a.only.split(",") if t] or [""]
+    items = [it for it in plan() if any(t in it[0] for t in only)]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     results = {}
     t_all = time.time()

@@ -12,13 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def one(B=8, R=512, prec="bf16"):
+def one(B=8, R=512, prec=None):
     import torch
     import bench
     import sfv_b200
 
-    bench.R = R
-    vae, rb, sd, rsd = bench.build_models(prec)
+    prec = prec or os.environ.get("SFV_PRECISION", "mixed")
+    B = int(os.environ.get("SFV_PROFILE_FRAMES", B))
+    vae, rb, sd, rsd = bench.build_models(prec, R)
     pipe = sfv_b200.FramePipeline(vae, rb, batch=B)
     u8 = sfv_b200.synthetic_frames(B, R, R, 1234, smooth=True).cuda()
     for _ in range(2):
@@ -47,6 +48,23 @@ def main():
     if "--one" in sys.argv:
         return one()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if "--current" in sys.argv:       # the product configuration (+ the fp32-stream A/B), every launch of every class
+        for name, env in (("mixed_stream16", {}), ("mixed_fp32stream", dict(SFV_STREAM16="0")), ("bf16", dict(SFV_PRECISION="bf16"))):
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], capture_output=True, text=True,
+                               env=dict(os.environ, **env), timeout=240)
+            got = [l for l in p.stdout.splitlines() if l.startswith("JSON::")]
+            if not got:
+                print(name, "FAILED", p.stderr[-800:]); continue
+            d = json.loads(got[0][6:])
+            names = ["tc_gemm", "igemm", "gn_stats", "gn_apply", "softmax", "other"]
+            agg = {}
+            for r in d["recs"]:
+                agg[names[r["cat"]]] = agg.get(names[r["cat"]], 0) + r["ms"]
+            print(f"== {name}: total {d['total_ms']:.2f} ms  " + " ".join(f"{k}={v:.2f}" for k, v in agg.items()), flush=True)
+            for i, r in enumerate(d["recs"]):
+                rate = r["work"] / r["ms"] / 1e9 if r["ms"] > 0 else 0
+                print(f"{i:3d} {names[r['cat']]:8s} {r['ms'] * 1e3:8.1f} us  {rate:8.1f} {'TF/s' if r['cat'] < 2 else 'GB/s'}  {r['tag']}")
+        return
     variants = [("ncta1_epi0_st0", dict(SFV_NCTA="1", SFV_EPI="0", SFV_FUSED_STATS="0")),
                 ("ncta1_epi0_st1", dict(SFV_NCTA="1", SFV_EPI="0", SFV_FUSED_STATS="1")),
                 ("ncta1_epi1_st0", dict(SFV_NCTA="1", SFV_EPI="1", SFV_FUSED_STATS="0")),

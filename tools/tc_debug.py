@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, bench, sfv_b200
 
-vae, rb, sd, rsd = bench.build_models("bf16")
+vae, rb, sd, rsd = bench.build_models(os.environ.get("SFV_PRECISION", "mixed"))
 pipe = sfv_b200.FramePipeline(vae, rb, batch=8)
 u8 = sfv_b200.synthetic_frames(8, 512, 512, 1234, smooth=True).cuda()
 for i in range(3):
