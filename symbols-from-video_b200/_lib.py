@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfv.so")
+LIB_PATH = os.environ.get("SFV_LIB_PATH") or os.path.join(_HERE, "libsfv.so")   # override: instrumented debug builds
 
 PREC_F32, PREC_BF16, PREC_FP16, PREC_MIXED = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_F32, "f32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_FP16, "f16": PREC_FP16,

@@ -818,6 +818,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = lane; t < ng2; t += 32) {
         const float val = acc_w[t];
         acc_w[t] = 0.f;
+
         const int grp = g0 + (t >> 1);
         if (grp < p.gn_groups)
           atomicAdd(&p.gn_stats[((long long)gn_img * p.gn_groups + grp) * 2 + (t & 1)],
@@ -880,14 +881,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = tc.tx, ty = tc.ty, img = tc.img;
       // the ring is only 1-2 chunks deep (shared memory goes to the operand pipeline), which would expose the
       // full DRAM latency of a tensor written two launches ago: pull the chunk one tile further ahead into L2
-      const int unit_pf = unit + unit_step;
-      const TileCoord tp = tile_coord<NCTA>(p, unit_pf < p.n_units ? unit_pf : unit, (int)rank);
-      const bool pf_ok = p.res_prefetch && unit_pf < p.n_units && tp.m_tile < p.n_tiles_m;
       if (elect_one_sync()) {
         const uint32_t bar = smem_u32(&res_bar_w[slot]);
         mbar_arrive_expect_tx(bar, (uint32_t)kResSlot);
         tma_load_4d(smem_u32(f32_w + slot * kResSlot), &tmR, bar, col0, tx * p.BW + wx, ty * p.BH + wy, img);
-        if (pf_ok)
+      }
+      if (p.res_prefetch) {       // experiment (off by default, measured slower): L2 prefetch one tile further ahead
+        const int unit_pf = unit + unit_step;
+        const TileCoord tp = tile_coord<NCTA>(p, unit_pf < p.n_units ? unit_pf : unit, (int)rank);
+        if (unit_pf < p.n_units && tp.m_tile < p.n_tiles_m && elect_one_sync())
           tma_prefetch_4d(&tmR, tp.n_tile * BLOCK_N + cbase + c * 32, tp.tx * p.BW + wx, tp.ty * p.BH + wy, tp.img);
       }
       __syncwarp();
@@ -1088,17 +1090,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t hb = h16_s + hslot * 2048 + lane * 64;
               if (p.out_16) {
                 if (p.out16_scale == 1.f) {
-                  uint32_t sat = 0;
+                  __half2 mx = __float2half2_rn(0.f);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const uint32_t w0 = pack2_16(f[8 * j], f[8 * j + 1], p.fmt_out), w1 = pack2_16(f[8 * j + 2], f[8 * j + 3], p.fmt_out);
                     const uint32_t w2 = pack2_16(f[8 * j + 4], f[8 * j + 5], p.fmt_out), w3 = pack2_16(f[8 * j + 6], f[8 * j + 7], p.fmt_out);
-                    // fp16 range check of the stored residual stream: a half at the saturation value (or inf / NaN) sets bit 15
-                    if (p.sat_check) sat |= ((w0 & 0x7FFF7FFFu) + 0x04010401u) | ((w1 & 0x7FFF7FFFu) + 0x04010401u) |
-                                            ((w2 & 0x7FFF7FFFu) + 0x04010401u) | ((w3 & 0x7FFF7FFFu) + 0x04010401u);
+                    // fp16 range check of the stored residual stream: running |max| of the packed pairs (one HMNMX2 per
+                    // word); the saturating conversion leaves 65504 in a half that overflowed
+                    if (p.sat_check) {
+                      mx = __hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w0)));
+                      mx = __hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w1)));
+                      mx = __hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w2)));
+                      mx = __hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w3)));
+                    }
                     sts128u(hb + ((j ^ sw16) << 4), w0, w1, w2, w3);
                   }
-                  if (p.sat_check && row_ok && (sat & 0x80008000u)) atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
+                  if (p.sat_check && row_ok && (__low2float(mx) >= 65504.f || __high2float(mx) >= 65504.f))
+                    atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
                 } else {
                   // scaled 16-bit copy of the residual stream (MIXED mode: fp16 x 2^-6); a value beyond the fp16
                   // range must not saturate silently -> error word (only the few launches that write such copies)

@@ -42,6 +42,31 @@ def main():
     assert z.shape[0] == 477 and out["flips_outside"] == 0
     if prec == "fp32":
         assert out["h_maxabs"] < 1e-5
+    # BASELINE configs[2]: the full-video precompute driver, frame range sharded over the ranks, latents + codes
+    # all-gathered in place, rank 0 writes the reference-format .npy (needs the sample video under oracle/_ref)
+    from oracle import ref_shim
+    video = ref_shim.video_path()
+    if video is not None:
+        import tempfile
+        tmp = tempfile.mkdtemp() if rank == 0 else None
+        box = [tmp]
+        dist.broadcast_object_list(box, src=0)
+        npy = os.path.join(box[0], "chinchess_perceps.npy")
+        r = sfv_b200.precompute_embeddings(sfv_b200.VideoSource(video), vae, rb, target_size=(W, 72), batch=64, rank=rank,
+                                           world=world, sample_posterior=False, fit="crop", n_decoders=2,
+                                           out_npy=npy if rank == 0 else None)
+        z2 = sfv_b200.unpack_codes(r.codes, chinchess.L).numpy()
+        d2 = z2 != g["z_hard"]
+        b2 = np.abs(g["h"]) < 1e-3
+        out2 = dict(rank=rank, precompute_frames=len(r.keys), flips_outside=int((d2 & ~b2).sum()), flips_inside=int((d2 & b2).sum()),
+                    stats={k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.stats.items() if "fps" in k})
+        print(out2, flush=True)
+        assert len(r.keys) == 480 and out2["flips_outside"] == 0
+        dist.barrier()
+        if rank == 0:
+            emb = np.load(npy, allow_pickle=True).item()
+            assert len(emb) == 480 and emb["0000000479.jpg"].shape == (1, 4, H // 8, W // 8) and emb["0000000000.jpg"].dtype == np.float32
+            print("precompute .npy written by rank 0:", len(emb), "keys", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -10,17 +10,10 @@ import torch
 import bench
 import sfv_b200
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+prec = sys.argv[1] if len(sys.argv) > 1 else "mixed"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 R = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-bench.R = R
-vae, rb, sd, rsd = bench.build_models(prec)
-if R != 512:
-    fh = R // 8
-    for _ in range(3):
-        fh = (fh - 1) // 2 + 1
-    rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, input_hw=(R // 8, R // 8))
-    rb.load_state_dict(sfv_b200.init_rbvae_state_dict(4, 25, (fh, fh), seed=1))
+vae, rb, sd, rsd = bench.build_models(prec, R)
 pipe = sfv_b200.FramePipeline(vae, rb, batch=B)
 u8 = sfv_b200.synthetic_frames(B, R, R, 1234, smooth=True).cuda()
 for _ in range(2):
