@@ -137,8 +137,11 @@ def make_weights(res):
     init every frame gets the same code and a code comparison would prove nothing."""
     import sfv_b200
     sd = sfv_b200.init_encoder_state_dict(0)
+    gains = dict(RB_GAINS)
+    if res >= 1024:
+        gains["fc_gain"] = 400.0      # fc sums 4x more features at 1024x1024: same recipe, flatter, so |h| errors stay < 1e-3
     rsd = sfv_b200.make_rbvae_responsive(sfv_b200.init_rbvae_state_dict(4, LATENT_DIM, (res // 64, res // 64), seed=1),
-                                         **RB_GAINS)
+                                         **gains)
     return sd, rsd
 
 

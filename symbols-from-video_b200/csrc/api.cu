@@ -204,10 +204,11 @@ int sfv_rbvae_create_ex(const SfvTensor* tensors, int32_t n_tensors, int32_t in_
   if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
   r->in_channels = in_channels; r->in_h = in_h; r->in_w = in_w;
   if (cudaGetDevice(&r->device) != cudaSuccess) { delete r; return fail(SFV_ERR_CUDA, "cudaGetDevice failed"); }
-  // MIXED: the RBVAE's conv inputs are ReLU'd conv outputs, i.e. not bounded by construction, so both operands of its
-  // two tensor-core convs take the range-safe format (a tcgen05 GEMM has one operand format)
-  r->prec = precision; r->fmt = precision == SFV_PREC_MIXED ? FMT_BF16 : fmt_of_precision(precision);
+  // MIXED: fp16 operands like the encoder's; the activation stores (conv.0's and the first tensor-core conv's ReLU'd
+  // outputs) are range-checked on the device, so an activation beyond +-65504 raises SFV_ERR_RANGE instead of saturating
+  r->prec = precision; r->fmt = fmt_of_precision(precision);
   r->fmt_act = r->fmt;
+  r->range_check = precision == SFV_PREC_MIXED;
   int st = rbvae_build(r, tensors, n_tensors);
   if (st != 0) { r->blob.release(); delete r; return st; }
   *out = r;

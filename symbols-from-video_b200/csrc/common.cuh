@@ -158,6 +158,7 @@ struct IgemmArgs {
   float in_scale;            // scale applied to x on load
   long long ldy;             // output row pitch (elements)
   int nchw_out;              // write y as NCHW [N,Cout,Ho,Wo] instead
+  int* err16;                // with fmt16 == FMT_F16: flag a y16 store beyond the fp16 range here (range-checked modes)
 };
 int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
 // y16 != nullptr: write to16(y16_scale * value) there (format fmt16) instead of the fp32 y
@@ -166,6 +167,9 @@ int launch_conv_in(const void* x, int src_kind, const float* w, const float* bia
 int launch_16_to_f32_scaled(const void* x, float* y, long long n, int fmt, float mul, cudaStream_t s);
 int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, int y16, int fmt, int N, int H, int W,
                     float in_scale, cudaStream_t s);
+// contrastive conv.0 on the tensor pipe, step 1: fp32 NCHW frames -> A[N*Ho*Wo][64] 16-bit rows of the stride-2 3x3 patch,
+// k < 27: hi(x), 27..53: lo(x) = x - hi (so the 16-bit operand carries ~fp32 input precision), 54..63: 0
+int launch_rb_im2col(const float* x, void* a16, int fmt, int N, int H, int W, float in_scale, cudaStream_t s);
 
 // ---- norm / elementwise ------------------------------------------------------
 // stats: double [N][G][2] accumulators (sum, sumsq) -- zeroed by the caller/kernel.
@@ -232,6 +236,7 @@ struct TcGemmArgs {
   // out_16 = to16(out16_scale * value) (0 means 1): the 16-bit copies of the residual stream are stored times 2^-6
   // in MIXED mode; a scaled fp16 store is range-checked in the epilogue (error site SITE_XCOPY).
   float out16_scale;
+  int sat_check;                     // range-check an (unscaled) fp16 out_16 store in the epilogue (error site SITE_XCOPY)
   double* gn_stats; int gn_cpg;      // optional fused GroupNorm partial sums [Nimg][Cout/gn_cpg][2] (pre-zeroed)
   // conv_in mode: instead of a 16-bit A tensor, uint8 HWC frames [Nimg][Ho][Wo][3]; the producer warp builds the
   // 3x3x3 patch rows (2u-255, zero padded, duplicated for the hi/lo weight split) straight into the swizzled A tile

@@ -158,7 +158,59 @@ rb_conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   }
 }
 
+// Contrastive conv.0 on the tensor pipe (contrastive_RBVAE_model.py:50-52), step 1 of 2: one thread per OUTPUT pixel gathers
+// its 3x3x3 stride-2 patch from the fp32 NCHW frame and writes one 128-byte row of the GEMM's A operand:
+// k = (r*3+s)*3 + c < 27 holds hi = to16(x), k + 27 holds lo = to16(x - hi), k >= 54 is zero.  The weights are [w | w | 0]
+// (rbvae.cu), so A . B^T = sum_k (hi + lo) w: the input enters with ~fp32 precision, only the weights are rounded.
+// Step 2 is the ordinary tcgen05 1x1 GEMM over these rows, IN PLACE: a tile's output rows (64 channels x 2 B) are its own
+// input rows, so no second buffer exists and the rows are still in L2 when they are rewritten.
+__global__ void __launch_bounds__(256) rb_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ a16, int fmt,
+                                                         int H, int W, int Ho, int Wo, float in_scale, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = (int)(i % Wo);
+  const int oy = (int)((i / Wo) % Ho);
+  const long long n = i / ((long long)Wo * Ho);
+  float v[27];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = 2 * oy - 1 + r;
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx) {
+      const int ix = 2 * ox - 1 + sx;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[(r * 3 + sx) * 3 + c] = ok ? __ldg(x + ((n * 3 + c) * H + iy) * W + ix) * in_scale : 0.f;
+    }
+  }
+  uint32_t wd[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) wd[k] = 0u;
+  uint16_t hv[54];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const uint16_t hi = f32_to_16(v[k], fmt);
+    hv[k] = hi;
+    hv[27 + k] = f32_to_16(v[k] - f16_to_32(hi, fmt), fmt);
+  }
+#pragma unroll
+  for (int k = 0; k < 54; ++k) wd[k >> 1] |= (uint32_t)hv[k] << (16 * (k & 1));
+  uint4* dst = a16 + i * 8;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[q] = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+}
+
 }  // namespace
+
+int launch_rb_im2col(const float* x, void* a16, int fmt, int N, int H, int W, float in_scale, cudaStream_t s) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo;
+  ProfScope prof(PROF_OTHER, (double)N * (3.0 * H * W * 4 + (double)Ho * Wo * 128), s, "rb_im2col");
+  rb_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, (uint4*)a16, fmt, H, W, Ho, Wo, in_scale, total);
+  SFV_LAUNCH_OK();
+  return 0;
+}
 
 // x fp32 NCHW [N,3,H,W]; w fp32 [27][64] (k = (r*3+s)*3 + c); y NHWC [N,Ho,Wo,64] fp32 (y16 == 0) or 16-bit.
 int launch_rb_conv0(const float* x, const float* w, const float* bias, void* y, int y16, int fmt, int N, int H, int W,

@@ -275,7 +275,7 @@ static int pick_block_n(int cout_pad) {
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats, const void* a2_16, float in_scale, float out16_scale, int res16, float res_mul) {
+            double* gn_stats, const void* a2_16, float in_scale, float out16_scale, int res16, float res_mul, int sat_check) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
@@ -329,7 +329,7 @@ int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, in
   a.Wo = Wo; a.Ho = Ho; a.Nimg = N; a.Cout = w.Cout;
   a.block_n = pick_block_n(w.cout_pad);
   a.alpha = 1.f / (w.w_scale * in_scale); a.bias = w.bias; a.residual = residual;   // exact: both are powers of two
-  a.res16 = res16; a.res_mul = res_mul;
+  a.res16 = res16; a.res_mul = res_mul; a.sat_check = sat_check;
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
   if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
     SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
@@ -359,9 +359,14 @@ int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, i
 
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
              int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s,
-             void* out16, int fmt16) {
+             void* out16, int fmt16, int range_check16) {
   IgemmArgs a;
   memset(&a, 0, sizeof(a));
+  if (range_check16) {
+    DevState* ds = nullptr;
+    SFV_TRY(dev_state(&ds));
+    a.err16 = ds->err_flag;
+  }
   a.x = in; a.src_kind = src_kind; a.w = w.w32; a.w_sk = w.Cout; a.w_sn = 1; a.w_batch = 0;
   a.bias = w.bias; a.residual = residual; a.y = out; a.y16 = out16; a.fmt16 = fmt16;
   a.N = N; a.H = H; a.W = W; a.Cin = w.Cin; a.Cout = w.Cout;

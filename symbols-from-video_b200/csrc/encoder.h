@@ -37,7 +37,7 @@ int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, i
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
             double* gn_stats = nullptr, const void* a2_16 = nullptr, float in_scale = 1.f, float out16_scale = 1.f,
-            int res16 = 0, float res_mul = 1.f);
+            int res16 = 0, float res_mul = 1.f, int sat_check = 0);
 inline int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
                    int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
                    double* gn_stats = nullptr, const void* a2_16 = nullptr) {
@@ -45,7 +45,7 @@ inline int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int 
 }
 int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, int stride, int pad_lo,
              int pad_hi, const float* residual, float* out, int relu, float in_scale, cudaStream_t s,
-             void* out16 = nullptr, int fmt16 = 0);
+             void* out16 = nullptr, int fmt16 = 0, int range_check16 = 0);
 int attention_f32(const float* q, const float* k, const float* v, float* O, float* S, int N, int L, int C,
                   float scale, cudaStream_t s);
 // fmt.a: format of the weights (they are the A operand here), fmt.b: of x16, fmt.out: of V^T
@@ -85,6 +85,9 @@ struct SfvRbvae {
   int fh = 0, fw = 0;                 // feature map after the three stride-2 convs
   sfv::DeviceBlob blob;
   sfv::ConvW c0, c1, c2;
+  sfv::ConvW c0_tc;                   // contrastive conv.0 as a 1x1 GEMM over im2col rows: [64][w | w | 0] (K = 64)
+  sfv::ConvW c0_tc2;                  // the same over pixel PAIRS: [128][128] = diag(c0_tc, c0_tc)
+  bool range_check = false;           // MIXED: fp16 activation stores are range-checked on the device
   float* fc_w = nullptr;              // [L][fh*fw*channels], permuted to NHWC flatten order
   float* fc_b = nullptr;
   float *w_ih = nullptr, *w_hh = nullptr, *lstm_b = nullptr;   // [layers][4L][L], [layers][4L]

@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const IgemmArgs a) {
       if (a.residual) v += a.residual[o];
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.y) a.y[o] = v;
-      if (a.y16) reinterpret_cast<uint16_t*>(a.y16)[o] = f32_to_16(v, a.fmt16);
+      if (a.y16) {
+        if (a.err16 && a.fmt16 == FMT_F16 && !(fabsf(v) <= 65504.f)) atomicCAS(a.err16, 0, kErrRangeBase + SITE_XCOPY);
+        reinterpret_cast<uint16_t*>(a.y16)[o] = f32_to_16(v, a.fmt16);
+      }
     }
   }
 }

@@ -44,6 +44,31 @@ int rbvae_build(SfvRbvae* r, const SfvTensor* t, int n) {
       return fail(SFV_ERR_MISSING_KEY, "rbvae: missing/mis-shaped %s", names[i]);
     SFV_TRY(make_conv_from_host(r->blob, ww->host_data, bb->host_data, r->channels, cin, 3, r->fmt,
                                 r->prec != SFV_PREC_F32 && i > 0, cw[i]));
+    if (i == 0 && r->prec != SFV_PREC_F32 && cin == 3 && r->channels == 64) {
+      // contrastive conv.0 (3 -> 64, stride 2) as a 1x1 GEMM over im2col rows [hi(x) 27 | lo(x) 27 | 0 10]: the weight
+      // row is [w | w | 0], k = (r*3+s)*3 + c  (launch_rb_im2col builds the matching A rows)
+      std::vector<float> w1((size_t)64 * 64, 0.f);
+      for (int o = 0; o < 64; ++o)
+        for (int c = 0; c < 3; ++c)
+          for (int t = 0; t < 9; ++t) {
+            const float v = ww->host_data[((size_t)o * 3 + c) * 9 + t];
+            w1[(size_t)o * 64 + t * 3 + c] = v;
+            w1[(size_t)o * 64 + 27 + t * 3 + c] = v;
+          }
+      SFV_TRY(make_conv_from_host(r->blob, w1.data(), bb->host_data, 64, 64, 1, r->fmt, true, &r->c0_tc));
+      // "pixel pairing": two horizontally adjacent output pixels form one 256-byte row, the weight is block diagonal
+      // diag(W, W).  Same bytes, but the GEMM runs as a 128-wide kernel with eight epilogue warps -- this layer is one
+      // k-chunk deep, i.e. purely epilogue bound, and the zero blocks cost nothing on the tensor pipe.
+      std::vector<float> w2((size_t)128 * 128, 0.f), b2(128);
+      for (int o = 0; o < 64; ++o) {
+        for (int k = 0; k < 64; ++k) {
+          w2[(size_t)o * 128 + k] = w1[(size_t)o * 64 + k];
+          w2[(size_t)(64 + o) * 128 + 64 + k] = w1[(size_t)o * 64 + k];
+        }
+        b2[o] = b2[64 + o] = bb->host_data[o];
+      }
+      SFV_TRY(make_conv_from_host(r->blob, w2.data(), b2.data(), 128, 128, 1, r->fmt, true, &r->c0_tc2));
+    }
     cin = r->channels;
   }
   {  // fc weight: reference flatten order is (C,H,W) (nn.Flatten on NCHW); ours is NHWC
@@ -131,9 +156,25 @@ int rbvae_encode(SfvRbvae* r, const float* x, int B, int T, float in_scale, cons
       // 16-bit operands for the two C->C convs (97 % of the RBVAE FLOPs) on the tcgen05 kernel;
       // conv.0 (Cin = 3 or 4) stays on CUDA cores and emits the 16-bit operand directly
       const TcFmt cf{r->fmt_act, r->fmt, r->fmt_act};
-      if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 1, r->fmt_act, nn, h[0], w[0], in_scale, s));
-      else SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt_act));
-      SFV_TRY(conv_tc(r->c1, cf, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s));
+      const int chk = r->range_check ? 1 : 0;
+      static const bool c0_tc_on = []() { const char* e = getenv("SFV_RB_CONV0_TC"); return !(e && atoi(e) == 0); }();
+      if (c0_direct && r->c0_tc.w16 && c0_tc_on) {
+        // conv.0 on the tensor pipe: im2col rows (hi | lo split of the fp32 input), then a 1x1 GEMM + bias + ReLU IN PLACE
+        // over those rows (a tile's 64-channel output row is its own 128-byte input row)
+        SFV_TRY(launch_rb_im2col(xi, a1i, r->fmt_act, nn, h[0], w[0], in_scale, s));
+        if (w[1] % 2 == 0 && r->c0_tc2.w16)
+          SFV_TRY(conv_tc(r->c0_tc2, cf, a1i, nn, h[1], w[1] / 2, 1, 0, 0, nullptr, nullptr, a1i, 1, s, nullptr, nullptr, 1.f,
+                          1.f, 0, 1.f, chk));
+        else
+          SFV_TRY(conv_tc(r->c0_tc, cf, a1i, nn, h[1], w[1], 1, 0, 0, nullptr, nullptr, a1i, 1, s, nullptr, nullptr, 1.f, 1.f,
+                          0, 1.f, chk));
+      } else if (c0_direct) {
+        SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 1, r->fmt_act, nn, h[0], w[0], in_scale, s));
+      } else {
+        SFV_TRY(conv_f32(r->c0, xi, SRC_NCHW_F32, nn, h[0], w[0], 2, 1, 1, nullptr, nullptr, 1, in_scale, s, a1i, r->fmt_act,
+                         chk));
+      }
+      SFV_TRY(conv_tc(r->c1, cf, a1i, nn, h[1], w[1], 2, 1, 1, nullptr, nullptr, a2i, 1, s, nullptr, nullptr, 1.f, 1.f, 0, 1.f, chk));
       SFV_TRY(conv_tc(r->c2, cf, a2i, nn, h[2], w[2], 2, 1, 1, nullptr, a1i, nullptr, 0, s));
     } else {
       if (c0_direct) SFV_TRY(launch_rb_conv0(xi, r->c0.w32, r->c0.bias, a1i, 0, r->fmt, nn, h[0], w[0], in_scale, s));

@@ -11,20 +11,22 @@ namespace {
 // HBM-bound skinny GEMM (L <= 256 outputs, K up to 262144 inputs per frame): every byte of x and of w is read from
 // HBM exactly once.  Split-K: block s owns the K-slice [s*KS, (s+1)*KS), keeps its slice of the weight in shared
 // memory (transposed to [k][l], so lane = l reads conflict-free and x is a broadcast) and streams the same slice of
-// EVERY frame past it, four frames at a time (register blocking: one 16-byte broadcast load of x feeds four FMAs).
+// EVERY frame past it, eight frames at a time (register blocking: two 16-byte broadcast loads of x feed eight FMAs).
 // It writes partial[s][n][l]; the sum over s (fixed order: deterministic, no atomics) and the bias are folded into
 // the LSTM kernel's load, so the logits never exist as a tensor of their own (fc -> LSTM -> threshold -> pack).
 constexpr int kFcThreads = 256;
-constexpr int kFcFrames = 4;
-constexpr int kFcWFloats = 16384;          // weight slice per block: 64 KB
+constexpr int kFcFrames = 8;
+constexpr int kFcWFloats = 8192;           // weight slice per block: 32 KB (four blocks per SM: the k loop is latency bound)
+constexpr int kFcFramesPerBlock = 32;      // frames one block streams past its weight slice (grid.y covers the rest)
 
 __global__ void __launch_bounds__(kFcThreads) fc_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                float* __restrict__ partial, int N, long long n_stride,
                                                                long long K, int L, int Lp, int KS) {
   extern __shared__ float fsm[];
-  float* wt = fsm;                                   // [KS][Lp]
-  float* xs = fsm + (size_t)KS * Lp;                 // [KS][4]
-  float* red = xs + (size_t)KS * kFcFrames;          // [8 warps][Lp][4]
+  const int Lw = Lp + 1;                             // padded row: the transposing stores below hit 32 different banks
+  float* wt = fsm;                                   // [KS][Lp + 1]
+  float* xs = fsm + (size_t)((KS * Lw + 3) & ~3);    // [KS][kFcFrames], 16-byte aligned
+  float* red = xs + (size_t)KS * kFcFrames;          // [8 warps][Lp][kFcFrames]
   const int s = blockIdx.x;
   const long long k0 = (long long)s * KS;
   const int kn = (int)min((long long)KS, K - k0);    // valid k in this slice
@@ -32,37 +34,68 @@ __global__ void __launch_bounds__(kFcThreads) fc_splitk_kernel(const float* __re
   // stage the weight slice, transposed: coalesced reads along k, writes [k][l]
   for (int i = threadIdx.x; i < Lp * KS; i += kFcThreads) {
     const int l = i / KS, k = i - l * KS;
-    wt[k * Lp + l] = (l < L && k < kn) ? w[(long long)l * K + k0 + k] : 0.f;
+    wt[k * Lw + l] = (l < L && k < kn) ? w[(long long)l * K + k0 + k] : 0.f;
   }
   const int lchunks = Lp >> 5;
   const int kw0 = warp * (KS >> 3), kw1 = kw0 + (KS >> 3);     // this warp's k sub-slice
-  for (int n0 = 0; n0 < N; n0 += kFcFrames) {
-    __syncthreads();                                 // previous group's xs / red are consumed (also covers the wt stage)
-    for (int i = threadIdx.x; i < kFcFrames * KS; i += kFcThreads) {
-      const int f = i / KS, k = i - f * KS;
-      const int n = n0 + f;
-      xs[k * kFcFrames + f] = (n < N && k < kn) ? x[(long long)n * K + k0 + k] : 0.f;
+  // the slice of the NEXT frame group is fetched into registers while the current one is being reduced, so the DRAM
+  // latency of the streaming operand is not paid once per group
+  const int per_thread = (kFcFrames * KS + kFcThreads - 1) / kFcThreads;      // <= 16 for KS <= 512
+  // blockIdx.y: this block's share of the frames (kFcFramesPerBlock), so the per-block chain of dependent groups stays short
+  const int n_begin = blockIdx.y * kFcFramesPerBlock;
+  const int n_end = min(N, n_begin + kFcFramesPerBlock);
+  float nxt[16];
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * kFcThreads;
+      float v = 0.f;
+      if (j < per_thread && i < kFcFrames * KS) {
+        const int f = i / KS, k = i - f * KS;
+        const int n = n0 + f;
+        if (n < n_end && k < kn) v = __ldg(x + (long long)n * K + k0 + k);
+      }
+      nxt[j] = v;
     }
+  };
+  fetch(n_begin);
+  for (int n0 = n_begin; n0 < n_end; n0 += kFcFrames) {
+    __syncthreads();                                 // previous group's xs / red are consumed (also covers the wt stage)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * kFcThreads;
+      if (j < per_thread && i < kFcFrames * KS) {
+        const int f = i / KS, k = i - f * KS;
+        xs[k * kFcFrames + f] = nxt[j];
+      }
+    }
+    if (n0 + kFcFrames < n_end) fetch(n0 + kFcFrames);
     __syncthreads();
     for (int lc = 0; lc < lchunks; ++lc) {
       const int l = lc * 32 + lane;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float a[kFcFrames];
+#pragma unroll
+      for (int f = 0; f < kFcFrames; ++f) a[f] = 0.f;
 #pragma unroll 4
       for (int k = kw0; k < kw1; ++k) {
-        const float4 xv = *reinterpret_cast<const float4*>(xs + k * kFcFrames);
-        const float wv = wt[k * Lp + l];
-        a0 = fmaf(xv.x, wv, a0); a1 = fmaf(xv.y, wv, a1); a2 = fmaf(xv.z, wv, a2); a3 = fmaf(xv.w, wv, a3);
+        const float4 x0 = *reinterpret_cast<const float4*>(xs + k * kFcFrames);
+        const float4 x1 = *reinterpret_cast<const float4*>(xs + k * kFcFrames + 4);
+        const float wv = wt[k * Lw + l];
+        a[0] = fmaf(x0.x, wv, a[0]); a[1] = fmaf(x0.y, wv, a[1]); a[2] = fmaf(x0.z, wv, a[2]); a[3] = fmaf(x0.w, wv, a[3]);
+        a[4] = fmaf(x1.x, wv, a[4]); a[5] = fmaf(x1.y, wv, a[5]); a[6] = fmaf(x1.z, wv, a[6]); a[7] = fmaf(x1.w, wv, a[7]);
       }
-      *reinterpret_cast<float4*>(red + ((size_t)warp * Lp + l) * 4) = make_float4(a0, a1, a2, a3);
+      float* rd = red + ((size_t)warp * Lp + l) * kFcFrames;
+      *reinterpret_cast<float4*>(rd) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(rd + 4) = make_float4(a[4], a[5], a[6], a[7]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Lp * kFcFrames; i += kFcThreads) {
-      const int l = i >> 2, f = i & 3;
+      const int l = i / kFcFrames, f = i - l * kFcFrames;
       const int n = n0 + f;
-      if (l < L && n < N) {
+      if (l < L && n < n_end) {
         float t = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < 8; ++wv) t += red[((size_t)wv * Lp + l) * 4 + f];
+        for (int wv = 0; wv < 8; ++wv) t += red[((size_t)wv * Lp + l) * kFcFrames + f];
         partial[((long long)s * n_stride + n) * L + l] = t;
       }
     }
@@ -165,6 +198,9 @@ __global__ void hamming_kernel(const uint32_t* a, int Na, const uint32_t* b, int
 void fc_plan(long long K, int L, int* KS, int* splits) {
   const int Lp = (L + 31) / 32 * 32;
   int ks = kFcWFloats / Lp;
+  if (ks > 512) ks = 512;                       // 8 frames x 512 k = 16 prefetch registers per thread
+  static const int ks_env = []() { const char* e = getenv("SFV_FC_KS"); return e ? atoi(e) : 0; }();   // experiments
+  if (ks_env > 0 && ks_env < ks) ks = ks_env;
   ks = ks / 8 * 8;                              // eight warps split the slice evenly
   if (ks < 8) ks = 8;
   if ((long long)ks > K) ks = (int)((K + 7) / 8 * 8);
@@ -179,15 +215,16 @@ int launch_fc(const float* x, const float* w, float* partial, int N, long long n
   int KS, splits;
   fc_plan(K, L, &KS, &splits);
   const int Lp = (L + 31) / 32 * 32;
-  const size_t smem = ((size_t)KS * Lp + (size_t)KS * kFcFrames + (size_t)8 * Lp * 4) * sizeof(float);
+  const size_t smem = ((size_t)((KS * (Lp + 1) + 3) & ~3) + (size_t)KS * kFcFrames + (size_t)8 * Lp * kFcFrames) * sizeof(float);
   static unsigned long long attr_devs = 0;
   int dev = 0;
   SFV_CUDA(cudaGetDevice(&dev));
   if (first_use_on_device(attr_devs, dev))
-    SFV_CUDA(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  SFV_CHECK(smem <= 100 * 1024, "fc: shared-memory plan too large (%zu)", smem);
+    SFV_CUDA(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  SFV_CHECK(smem <= 160 * 1024, "fc: shared-memory plan too large (%zu)", smem);
   ProfScope prof(PROF_OTHER, ((double)N * K + (double)L * K) * 4.0, s);
-  fc_splitk_kernel<<<splits, kFcThreads, smem, s>>>(x, w, partial, N, n_stride, K, L, Lp, KS);
+  fc_splitk_kernel<<<dim3(splits, (N + kFcFramesPerBlock - 1) / kFcFramesPerBlock), kFcThreads, smem, s>>>(x, w, partial, N, n_stride, K,
+                                                                                                        L, Lp, KS);
   SFV_LAUNCH_OK();
   return 0;
 }

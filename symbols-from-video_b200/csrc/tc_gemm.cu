@@ -1518,6 +1518,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     p.sat_check = fmt_out == FMT_F16;
     p.out16_scale = 1.f;
   }
+  if (a.sat_check && a.out_16 && fmt_out == FMT_F16 && a.block_n >= 32) p.sat_check = 1;
 
   p.gn_stats = a.gn_stats; p.gn_cpg = a.gn_cpg; p.gn_groups = a.gn_cpg ? a.Cout / a.gn_cpg : 0;
   if (a.gn_stats)
