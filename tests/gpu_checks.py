@@ -336,6 +336,35 @@ def check_pipeline(prec="fp16", B=6, R=64, L=25, seed=0, batch=4):
     return out
 
 
+def check_encode_host_sampling(prec="fp32"):
+    """FramePipeline.encode_host(sample_posterior=True) stores what the reference's precompute stores,
+    scale * posterior.sample() (get_percep_embeddings.py:100-101): one torch.randn(1,4,h,w) per frame from the global
+    CPU generator in frame order (distributions.py:36), across sub-batch boundaries; an explicit noise tensor gives
+    the same result, and the default (mode) is unchanged."""
+    vae, sd = make_vae(prec, 0)
+    B, R = 7, 32
+    u8 = frames.synthetic_frames(B, R, R, 31, smooth=True)
+    post = kl_f8.encode(frames.normalise_u8(u8), sd)
+    torch.manual_seed(99)
+    noise = torch.cat([torch.randn(1, 4, R // 8, R // 8) for _ in range(B)])
+    ref = kl_f8.first_stage_encoding(post, noise=noise)
+    pipe = sfv_b200.FramePipeline(vae, None, batch=8)
+    pipe.host_batch = 3                                     # 3 + 3 + 1 frames: draws must continue across sub-batches
+    torch.manual_seed(99)
+    a = pipe.encode_host(torch.from_numpy(u8), sample_posterior=True).latents
+    after = torch.rand(1)
+    torch.manual_seed(99)
+    for _ in range(B):
+        torch.randn(1, 4, R // 8, R // 8)
+    assert torch.equal(after, torch.rand(1)), "global RNG not consumed like the reference's loop"
+    b = pipe.encode_host(torch.from_numpy(u8), noise=noise).latents
+    c = pipe.encode_host(torch.from_numpy(u8)).latents
+    out = dict(prec=prec, sampled=rel_l2(a, ref), explicit_noise=rel_l2(b, ref), mode=rel_l2(c, kl_f8.first_stage_encoding(post, use_mode=True)))
+    assert torch.equal(a, b), out
+    assert max(out["sampled"], out["mode"]) <= latent_gate(prec), out
+    return out
+
+
 def check_full_size_properties(prec="bf16", B=4, R=512):
     """BASELINE config-2 frame size, where the CPU oracle is too slow: size-independent
     properties -- batch permutation equivariance, determinism, finite outputs, logvar clamp range."""

@@ -172,6 +172,15 @@ def test_all_gather_ragged_gloo_world2(tmp_path):
         codes = sfv_b200.all_gather_ragged(full_codes[lo:hi].clone(), counts)
         lat = sfv_b200.all_gather_ragged(full_lat[lo:hi].clone(), counts)
         assert torch.equal(codes, full_codes) and torch.equal(lat, full_lat), (r, codes)
+        # in-place gather of pre-filled blocks (what encode_sharded / precompute / bench do: the kernels write this
+        # rank's block of the gather buffer, one collective per tensor, async handle), ragged tail padded to mx rows
+        mx = max(counts)
+        buf = torch.full((w * mx, 4, 2, 2), -1.0)
+        buf[r * mx:r * mx + (hi - lo)] = full_lat[lo:hi]
+        work = sfv_b200.all_gather_slices(buf, r, w, async_op=True)
+        work.wait()
+        got = torch.cat([buf[i * mx:i * mx + counts[i]] for i in range(w)])
+        assert torch.equal(got, full_lat), (r, got)
         dist.destroy_process_group()
         print("rank", r, "ok", lo, hi)
     """))

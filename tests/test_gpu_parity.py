@@ -163,3 +163,8 @@ def test_resident_dataset_on_device():
                                       pytest.param("bf16", 512, 4, marks=BF16_MISS.marks)])
 def test_full_size_against_cuda_fp32_oracle(prec, R, B):
     print(_c().check_full_size_oracle(prec, R, B))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "mixed"])
+def test_encode_host_posterior_sampling(prec):
+    print(_c().check_encode_host_sampling(prec))
