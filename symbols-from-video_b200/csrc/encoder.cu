@@ -378,6 +378,9 @@ int conv_f32(const ConvW& w, const void* in, int src_kind, int N, int H, int W, 
 }
 
 // ------------------------------------------------------------------ forward
+// SFV_ATTN_FUSED=0 falls back to materialised fp32 scores + a separate softmax kernel (A/B measurements)
+static const bool g_attn_fused = []() { const char* e = getenv("SFV_ATTN_FUSED"); return !(e && atoi(e) == 0); }();
+
 namespace {
 
 struct Plan {
@@ -404,12 +407,15 @@ void make_plan(bool tc, bool s16, int Bc, int H, int W, Arena& ar, Plan* p) {
   p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   p->stats2 = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
   const size_t Lp = (L + 7) / 8 * 8;                  // row pitch of S / P / V^T (16-byte rows for TMA)
-  const size_t per_img = L * Lp * (tc ? 6 : 4);
-  size_t na = (size_t)(1536ull << 20) / (per_img ? per_img : 1);
+  // the fp32 score matrix S exists only in the check mode and in the unfused A/B path; the tensor-core path keeps the
+  // scores on chip and stores P (16 bit) only
+  const bool need_S = !tc || !g_attn_fused;
+  const size_t per_img = L * Lp * ((need_S ? 4 : 0) + (tc ? 2 : 0));
+  size_t na = (size_t)(1024ull << 20) / (per_img ? per_img : 1);
   if (na < 1) na = 1;
   if (na > (size_t)Bc) na = Bc;
   p->attn_chunk = (int)na;
-  p->S = (float*)ar.take(na * L * Lp * 4);
+  p->S = need_S ? (float*)ar.take(na * L * Lp * 4) : nullptr;
   p->P = tc ? ar.take(na * L * Lp * 2) : nullptr;
   p->moments = (float*)ar.take((size_t)Bc * L * 8 * 4);
 }
@@ -537,8 +543,6 @@ struct Fwd {
 
 }  // namespace
 
-// SFV_ATTN_FUSED=0 falls back to materialised fp32 scores + a separate softmax kernel (A/B measurements)
-static const bool g_attn_fused = []() { const char* e = getenv("SFV_ATTN_FUSED"); return !(e && atoi(e) == 0); }();
 
 // Tensor-core attention core for a chunk of images whose score matrices fit S/P:
 //   S = scale * Q K^T (fp32) ; P = softmax(S) (16-bit) ; O = P V + b_v (16-bit)
