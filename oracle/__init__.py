@@ -28,4 +28,9 @@ container from /root/reference (``ref_shim.py``), with the vectors committed
 under ``tests/golden/`` together with the generating script
 (``oracle/make_golden.py``).  ``tests/test_oracle_golden.py`` re-checks the
 oracle against those vectors without needing /root/reference.
+
+The reference itself also travels: ``build_ref.py`` (run by ``__graft_entry__.build()`` in the build container)
+copies the 8 hot-path reference files and the sample video byte for byte into the git-ignored ``oracle/_ref/``;
+``ref_shim.py`` imports the unmodified classes from there when /root/reference is absent (GPU box), which is what
+``bench.py --impl reference`` / its ``cpu_baseline`` leg time (``kind: "reference"``) next to the port.
 """

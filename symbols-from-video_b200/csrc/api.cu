@@ -124,6 +124,11 @@ int sfv_encoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t prec
     e->xc_scale = 1.f / 64.f;
     e->range_check = true;
     e->stream16 = true;
+    // GroupNorm+SiLU inside the consuming conv (transform warps, HALO BLOCK_N = 256 launches): bit-identical to the
+    // stand-alone pass but measured SLOWER on B200 (three 65 KB stages cannot hide load + transform latency),
+    // so it is opt-in
+    e->gn_fuse = false;
+    if (const char* v = getenv("SFV_GN_FUSE")) e->gn_fuse = atoi(v) != 0;
     if (const char* v = getenv("SFV_XC_SCALE_LOG2")) e->xc_scale = ldexpf(1.f, -atoi(v));
     if (const char* v = getenv("SFV_STREAM16")) e->stream16 = atoi(v) != 0;    // A/B: 0 keeps the fp32 residual stream
   }

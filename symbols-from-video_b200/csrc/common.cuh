@@ -237,6 +237,11 @@ struct TcGemmArgs {
   // in MIXED mode; a scaled fp16 store is range-checked in the epilogue (error site SITE_XCOPY).
   float out16_scale;
   int sat_check;                     // range-check an (unscaled) fp16 out_16 store in the epilogue (error site SITE_XCOPY)
+  // Fused GroupNorm(32)(+SiLU) of the A operand (XF kernels): `a` is the RAW 16-bit input, normalised in shared memory
+  // by transform warps with these statistics [Nimg][32][2] / affine.  xf_in_mul: multiplier of the stored input (64 for
+  // the scaled residual stream).  Only the HALO BLOCK_N = 256 pair kernel has the variant: launch_tc_gemm returns
+  // TC_NOT_FUSABLE (and launches nothing) for any other launch, the caller then runs the stand-alone apply pass.
+  const double* xf_stats; const float* xf_gamma; const float* xf_beta; float xf_in_mul; int xf_silu; int xf_check;
   double* gn_stats; int gn_cpg;      // optional fused GroupNorm partial sums [Nimg][Cout/gn_cpg][2] (pre-zeroed)
   // conv_in mode: instead of a 16-bit A tensor, uint8 HWC frames [Nimg][Ho][Wo][3]; the producer warp builds the
   // 3x3x3 patch rows (2u-255, zero padded, duplicated for the hi/lo weight split) straight into the swizzled A tile
@@ -245,6 +250,7 @@ struct TcGemmArgs {
   // over the n-tiles inside one CTA pair; needs out_16 only: no bias / residual / fp32 output / statistics)
   int softmax_mode;
 };
+constexpr int TC_NOT_FUSABLE = 1;
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s);
 int tc_check_device_error(cudaStream_t s);   // sync + read the watchdog flag
 

@@ -275,7 +275,8 @@ static int pick_block_n(int cout_pad) {
 // conv on the tensor-core path.  in16: NHWC 16-bit [N,H,W,Cin].
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
-            double* gn_stats, const void* a2_16, float in_scale, float out16_scale, int res16, float res_mul, int sat_check) {
+            double* gn_stats, const void* a2_16, float in_scale, float out16_scale, int res16, float res_mul, int sat_check,
+            const XfIn* xf) {
   SFV_CHECK(w.w16 != nullptr, "conv_tc: layer has no 16-bit weights (Cin=%d)", w.Cin);
   const int ks = w.ks, Cin = w.Cin;
   int Ho, Wo;
@@ -330,6 +331,10 @@ int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, in
   a.block_n = pick_block_n(w.cout_pad);
   a.alpha = 1.f / (w.w_scale * in_scale); a.bias = w.bias; a.residual = residual;   // exact: both are powers of two
   a.res16 = res16; a.res_mul = res_mul; a.sat_check = sat_check;
+  if (xf) {
+    a.xf_stats = xf->stats; a.xf_gamma = xf->gamma; a.xf_beta = xf->beta; a.xf_in_mul = xf->in_mul; a.xf_silu = xf->silu;
+    a.xf_check = xf->check;
+  }
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
   if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
     SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
@@ -442,14 +447,14 @@ struct Fwd {
   // A convolution that produces the next residual-stream tensor `xo` (+ optional residual `res` from the stream,
   // + optional 16-bit operand copy for the fp32-stream mode): handles both stream representations.
   int conv_x(const ConvW& w, const void* in_op, float in_scale, int H, int W, int stride, const void* res, void* xo,
-             void* copy, const void* a2 = nullptr) {
+             void* copy, const void* a2 = nullptr, const XfIn* xf = nullptr) {
     const int pad_lo = (w.ks == 3 && stride == 1) ? 1 : 0;
     const int pad_hi = (w.ks == 3) ? 1 : 0;
     const float xs = e->xc_scale;
     if (!tc) return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, (const float*)res, (float*)xo, 0, 1.f, s);
     if (s16)
       return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, nullptr, xo, 0, s, sx(), a2, in_scale, xs,
-                     res != nullptr, 1.f / xs);
+                     res != nullptr, 1.f / xs, 0, xf);
     return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, (float*)xo, copy, 0, s, sx(), a2, in_scale, xs);
   }
   // formats of a conv whose A operand is a GroupNorm / conv1 output (fmt) and whose 16-bit output is one too
@@ -476,23 +481,45 @@ struct Fwd {
   int resblock(const ResW& r, const void* x, const void* x_op, int H, int W, void* xo, bool want_copy,
                const void** xo_op) {
     const long long HW = (long long)H * W;
-    SFV_TRY(gn_x(r.n1, x, HW, 1, pl.oa));
-    SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
-    SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
+    // conv1 = conv(silu(GN1(x))), conv2 input = silu(GN2(h)).  With a 16-bit stream both GroupNorms can run inside the
+    // consuming conv (transform warps normalise the raw A tile in shared memory) wherever that kernel variant exists;
+    // elsewhere the stand-alone apply pass writes the operand first.
+    const bool fuse = s16 && e->gn_fuse && e->fused_stats;
+    XfIn xf1{sx(), r.n1.gamma, r.n1.beta, 1.f / e->xc_scale, 1, e->range_check ? 1 : 0};
+    XfIn xf2{sh(), r.n2.gamma, r.n2.beta, 1.f, 1, e->range_check ? 1 : 0};
+    // (with fusion on, conv1's epilogue range-checks h as it stores it: the stand-alone apply pass that used to read h
+    // and check it may not run)
+    const int chk_h = (fuse && e->range_check) ? 1 : 0;
+    int st = fuse ? conv_tc(r.c1, cf(), x, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, sh(), nullptr, 1.f, 1.f, 0, 1.f, chk_h, &xf1)
+                  : TC_NOT_FUSABLE;
+    if (st == TC_NOT_FUSABLE) {
+      SFV_TRY(gn_x(r.n1, x, HW, 1, pl.oa));
+      if (tc) SFV_TRY(conv_tc(r.c1, cf(), pl.oa, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, sh(), nullptr, 1.f, 1.f, 0, 1.f, chk_h));
+      else SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
+    } else if (st != 0) {
+      return st;
+    }
     const void* res = x;
     void* copy = (tc && want_copy && !s16) ? pl.x16 : nullptr;
     const float xs = e->xc_scale;              // the 16-bit copies of x (or x itself) hold xs * x
-    if (r.has_nin && tc && e->fuse_nin) {
-      // x' = nin(x) + conv2(a2): one GEMM, the 1x1 shortcut rides along as extra K chunks read from x's 16-bit copy
-      // (its weights carry 1 / xs, see get_res)
-      SFV_TRY(conv_x(r.c2n, pl.oa, 1.f, H, W, 1, nullptr, xo, copy, x_op));
-    } else {
+    auto conv2 = [&](const void* in, const XfIn* xf) -> int {
+      if (r.has_nin && tc && e->fuse_nin) {
+        // x' = nin(x) + conv2(a2): one GEMM, the 1x1 shortcut rides along as extra K chunks read from x's 16-bit copy
+        // (its weights carry 1 / xs, see get_res)
+        return conv_x(r.c2n, in, 1.f, H, W, 1, nullptr, xo, copy, x_op, xf);
+      }
       if (r.has_nin) {
         SFV_TRY(conv_x(r.nin, x_op, tc ? xs : 1.f, H, W, 1, nullptr, xo, nullptr));
         res = xo;
       }
-      SFV_TRY(conv_x(r.c2, pl.oa, 1.f, H, W, 1, res, xo, copy));
+      return conv_x(r.c2, in, 1.f, H, W, 1, res, xo, copy, nullptr, xf);
+    };
+    st = fuse ? conv2(pl.ob, &xf2) : TC_NOT_FUSABLE;
+    if (st == TC_NOT_FUSABLE) {
+      SFV_TRY(gn(r.n2, pl.ob, tc, HW, 1, pl.oa, sh()));
+      st = conv2(pl.oa, nullptr);
     }
+    if (st != 0) return st;
     *xo_op = tc ? (s16 ? (const void*)xo : (const void*)copy) : (const void*)xo;
     return 0;
   }

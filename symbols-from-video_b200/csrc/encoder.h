@@ -28,6 +28,8 @@ int make_conv_from_host(DeviceBlob& blob, const float* w, const float* b, int Co
                         int fmt, bool want16, ConvW* out);
 // 16-bit formats of one tensor-core GEMM: A operand, B operand, 16-bit output
 struct TcFmt { int a, b, out; };
+// GroupNorm(32)(+SiLU) to be applied to the conv's raw 16-bit input inside the kernel (TcGemmArgs::xf_*)
+struct XfIn { const double* stats; const float* gamma; const float* beta; float in_mul; int silu; int check; };
 inline TcFmt tcfmt(int f) { return TcFmt{f, f, f}; }
 int make_conv_in_u8(DeviceBlob& blob, const float* w_oihw, int fmt, ConvW* out);
 int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, int W, float* out_f32, double* gn_stats,
@@ -37,7 +39,7 @@ int conv_in_tc(const ConvW& w, int fmt, const unsigned char* u8, int N, int H, i
 int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
             int pad_hi, const void* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
             double* gn_stats = nullptr, const void* a2_16 = nullptr, float in_scale = 1.f, float out16_scale = 1.f,
-            int res16 = 0, float res_mul = 1.f, int sat_check = 0);
+            int res16 = 0, float res_mul = 1.f, int sat_check = 0, const XfIn* xf = nullptr);
 inline int conv_tc(const ConvW& w, int fmt, const void* in16, int N, int H, int W, int stride, int pad_lo,
                    int pad_hi, const float* residual, float* out_f32, void* out_16, int relu, cudaStream_t s,
                    double* gn_stats = nullptr, const void* a2_16 = nullptr) {
@@ -68,6 +70,7 @@ struct SfvEncoder {
   float xc_scale = 1.f;
   bool range_check = false;    // MIXED: fp16 store sites are range-checked on the device
   bool stream16 = false;       // MIXED: the residual stream x itself is stored as fp16 * xc_scale (no fp32 copy of x in HBM)
+  bool gn_fuse = false;        // 16-bit stream: GroupNorm+SiLU applied inside the consuming conv where a transform variant exists
   bool fuse_nin = true;        // nin_shortcut folded into conv2's GEMM (tensor-core modes)
   bool fused_stats = true;     // GroupNorm statistics from the producing kernel's epilogue (tensor-core modes)
   bool conv_in_tc = true;      // uint8-fed conv_in on the tensor pipe (tensor-core modes; SFV_CONV_IN_TC=0: CUDA cores)

@@ -78,6 +78,11 @@ struct TcParams {
   // stream scale s, so the finished value IS the stored value (no per-element multiply); GroupNorm partial sums are
   // un-scaled when flushed (stat_mul = 1/s for sums, its square for sums of squares; exact, s is a power of two)
   float bias_mul, stat_mul; int sat_check;
+  // XF kernels (GroupNorm + SiLU applied to the A operand inside the kernel, see the transform warps): statistics of
+  // the raw input [img][32][2] (sum, sum of squares), affine, element count per (image, channel), multiplier of the
+  // stored input (64 for the scaled residual stream), SiLU on/off, range check of the fp16 inputs / outputs
+  const double* xf_stats; const float* xf_gamma; const float* xf_beta;
+  long long xf_hw; int xf_cin; float xf_in_mul; int xf_silu; int xf_check;
   long long ldo;
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
@@ -509,7 +514,8 @@ __device__ __forceinline__ void conv_in_store_rows(const float (&v)[3][18], uint
   }
 }
 
-template <int BLOCK_N, int NCTA, bool HALO = false>
+constexpr int kXfWarps = 4;             // transform warps of an XF kernel
+template <int BLOCK_N, int NCTA, bool HALO = false, bool XF = false>
 struct Cfg {
   static constexpr int kGroup = HALO ? 3 : 1;                           // filter taps per pipeline stage
   static constexpr int kATxBytes = HALO ? 130 * 128 : kBlockM * kBlockK * 2;
@@ -521,7 +527,8 @@ struct Cfg {
   // BLOCK_N = 256 kernels (attention GEMMs, 64x64 convs: short K, epilogue-bound with four warps)
   static constexpr int kSets = (BLOCK_N == 128 || (BLOCK_N == 256 && !HALO)) ? 2 : 1;
   static constexpr int kEpiWarps = 4 * kSets;
-  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps + (XF ? 32 * kXfWarps : 0);
+  static constexpr int kXfBytes = XF ? 4096 : 0;       // per-image (scale, shift) table of the fused GroupNorm, [Cin <= 512] float2
   // The staging rings are sized per launch (a conv that writes only 16-bit outputs needs no fp32 ring), and
   // whatever shared memory is left becomes pipeline stages: res_bufs fp32 slots (0, 2 or 3) and h16_slots
   // (0 or 2) per epilogue warp, see smem_plan().
@@ -531,22 +538,73 @@ struct Cfg {
     return BLOCK_N >= 32 ? kEpiWarps * (res_bufs * res_slot + h16_slots * 2048) : 0;
   }
   static __host__ constexpr int stages_for(int res_bufs, int h16_slots, int res_slot = 4096) {
-    const int n = (kSmemLimit - 1024 - kAuxBytes - epi_bytes(res_bufs, h16_slots, res_slot)) / kStageBytes;
+    const int n = (kSmemLimit - 1024 - kAuxBytes - kXfBytes - epi_bytes(res_bufs, h16_slots, res_slot)) / kStageBytes;
     return n > kMaxStages ? kMaxStages : n;
   }
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
   static __host__ constexpr int smem_bytes(int stages, int res_bufs, int h16_slots, int res_slot = 4096) {
-    return stages * kStageBytes + epi_bytes(res_bufs, h16_slots, res_slot) + kAuxBytes + 1024 /*align slack*/;
+    return stages * kStageBytes + epi_bytes(res_bufs, h16_slots, res_slot) + kAuxBytes + kXfBytes + 1024 /*align slack*/;
   }
 };
 
-template <int BLOCK_N, int NCTA, bool HALO>
-__global__ void __launch_bounds__(Cfg<BLOCK_N, NCTA, HALO>::kThreads, 1)
+__device__ __forceinline__ float xf_silu_tanh(float t) {      // t * sigmoid(t) = h + h tanh(h), h = t/2 (as norm.cu's silu_tanh)
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
+// Three of a transform thread's 16-byte units (rows r, r + 16, r + 32 of the A box): loads back to back, arithmetic with
+// all 24 values independent, stores.  Kept a compact, rolled-loop body on purpose: the fully unrolled nine-unit version
+// is ~1000 straight-line instructions per stage and ran instruction-fetch bound (2850 cycles per stage measured).
+template <int FMT>
+__device__ __forceinline__ void xf_units3(uint32_t sa, int r_first, int c_log, int x_first, int Wo, const float (&sc)[8],
+                                          const float (&sf)[8], bool silu, bool chk, __half2& mx_out) {
+  uint32_t w[3][4];
+  bool on[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int r = r_first + 16 * u;
+    const int px = x_first + r;
+    on[u] = r < 130 && px >= 0 && px < Wo;
+    if (on[u]) {
+      const float4 q = lds128(sa + r * 128 + ((c_log ^ (r & 7)) << 4));
+      w[u][0] = __float_as_uint(q.x); w[u][1] = __float_as_uint(q.y); w[u][2] = __float_as_uint(q.z); w[u][3] = __float_as_uint(q.w);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    if (on[u]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a, b;
+        unpack2_16(w[u][i], FMT, a, b);
+        a = fmaf(a, sc[2 * i], sf[2 * i]); b = fmaf(b, sc[2 * i + 1], sf[2 * i + 1]);
+        if (silu) { a = xf_silu_tanh(a); b = xf_silu_tanh(b); }
+        w[u][i] = pack2_16(a, b, FMT);
+      }
+      if (FMT == FMT_F16 && chk) {
+        mx_out = __hmax2(__hmax2(mx_out, __habs2(*reinterpret_cast<const __half2*>(&w[u][0]))),
+                         __habs2(*reinterpret_cast<const __half2*>(&w[u][1])));
+        mx_out = __hmax2(__hmax2(mx_out, __habs2(*reinterpret_cast<const __half2*>(&w[u][2]))),
+                         __habs2(*reinterpret_cast<const __half2*>(&w[u][3])));
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int r = r_first + 16 * u;
+    if (on[u]) sts128u(sa + r * 128 + ((c_log ^ (r & 7)) << 4), w[u][0], w[u][1], w[u][2], w[u][3]);
+  }
+}
+
+template <int BLOCK_N, int NCTA, bool HALO, bool XF = false>
+__global__ void __launch_bounds__(Cfg<BLOCK_N, NCTA, HALO, XF>::kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO32,
                const __grid_constant__ CUtensorMap tmO16, const TcParams p) {
-  using C = Cfg<BLOCK_N, NCTA, HALO>;
+  using C = Cfg<BLOCK_N, NCTA, HALO, XF>;
   // NCTA == 2: the kernel runs as clusters of two CTAs (one SM pair) that share one
   // 256-pixel x BLOCK_N tile; rank 0 issues the MMAs for both (tcgen05 cta_group::2).
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
@@ -573,10 +631,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * C::kMaxStages;
   uint64_t* tempty_bar = bars + 2 * C::kMaxStages + 2;
   uint64_t* res_bar = bars + 2 * C::kMaxStages + 4;                        // [epilogue warps][kMaxResBufs]
-  uint32_t* tmem_ptr = (uint32_t*)(res_bar + C::kEpiWarps * kMaxResBufs);
+  // XF: afull_bar = this CTA's A box has landed (local), xf_bar = the A tiles of the stage are transformed (leader's)
+  uint64_t* afull_bar = res_bar + C::kEpiWarps * kMaxResBufs;
+  uint64_t* xf_bar = afull_bar + C::kMaxStages;
+  uint32_t* tmem_ptr = (uint32_t*)(XF ? xf_bar + C::kMaxStages : afull_bar);
   volatile int* abort_flag = (volatile int*)(tmem_ptr + 1);
   float* gn_acc = (float*)((uint8_t*)bars + 512);        // [epilogue warps][512 / warps floats]: (sum, sumsq) per group
   float* bias_all = gn_acc + 512;                        // [epilogue warps][1024 / warps floats]
+  float2* xf_tab = (float2*)(bias_all + 1024);           // XF: [Cin] (scale, shift) of the current image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -591,6 +653,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(smem_u32(&tempty_bar[i]), C::kEpiWarps * NCTA);
     }
     for (int i = 0; i < C::kEpiWarps * kMaxResBufs; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    if constexpr (XF) {
+      for (int i = 0; i < num_stages; ++i) {
+        mbar_init(smem_u32(&afull_bar[i]), 1);
+        mbar_init(smem_u32(&xf_bar[i]), kXfWarps * NCTA);
+      }
+    }
     *abort_flag = 0;
     fence_barrier_init();
   }
@@ -687,7 +755,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (elect_one_sync()) {
               // HALO: tap is the left tap of a filter row; its box is 130 pixels wide and serves taps tap..tap+2
-              if constexpr (NCTA == 2) {
+              if constexpr (NCTA == 2 && XF) {
+                // XF: this CTA's A box completes on its OWN barrier (its transform warps wait there); the weight tiles
+                // of both CTAs complete on the leader's full barrier as usual
+                const uint32_t ab = smem_u32(&afull_bar[stage]);
+                mbar_arrive_expect_tx(ab, C::kATxBytes);
+                tma_load_5d(sa, &tmA, ab, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kGroup * C::kBBytes);
+#pragma unroll
+                for (int g = 0; g < C::kGroup; ++g)
+                  tma_load_3d_2cta(sa + C::kABytes + g * C::kBBytes, &tmB, fb, p.tap_k[tap + g] + kc * kBlockK,
+                                   n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), p.b_batched ? img : 0);
+              } else if constexpr (NCTA == 2) {
                 // the leader's barrier collects the bytes of both CTAs' loads
                 if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kTxBytes);
                 tma_load_5d_2cta(sa, &tmA, fb, p.tap_o[tap][0] + kc * kBlockK, c1, c2, c3, c4);
@@ -718,7 +797,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (elect_one_sync()) {
-              if constexpr (NCTA == 2) {
+              if constexpr (NCTA == 2 && XF) {
+                const uint32_t ab = smem_u32(&afull_bar[stage]);
+                mbar_arrive_expect_tx(ab, kBlockM * kBlockK * 2);
+                tma_load_5d(sa, &tmA2, ab, kc * kBlockK, base[1], base[2], base[3], base[4]);
+                if (rank == 0) mbar_arrive_expect_tx(fb, 2 * C::kBBytes);
+                tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK,
+                                 n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2), 0);
+              } else if constexpr (NCTA == 2) {
                 if (rank == 0) mbar_arrive_expect_tx(fb, 2 * kTx1);
                 tma_load_5d_2cta(sa, &tmA2, fb, kc * kBlockK, base[1], base[2], base[3], base[4]);
                 tma_load_3d_2cta(sa + C::kABytes, &tmB, fb, p.a2_k0 + kc * kBlockK,
@@ -757,6 +843,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ok = mbar_wait(smem_u32(&full_bar[stage]), phase, abort_flag, p.err, 3);
           if (p.dbg) t_full += clock64() - tw;
           if (!ok) break;
+          if constexpr (XF) {      // the A tiles of both CTAs have been normalised in place
+            ok = mbar_wait(smem_u32(&xf_bar[stage]), phase, abort_flag, p.err, 7);
+            if (!ok) break;
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const int main_iters = k_iters - p.a2_kchunks;
@@ -793,6 +883,98 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 2] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 3] = t_full; p.dbg[blockIdx.x * 16 + 4] = t_tempty; }
+    }
+  } else if (XF && warp >= 2 + C::kEpiWarps) {
+    // ===================== transform warps (XF kernels): GroupNorm (+SiLU) of the A operand, in place ==============
+    // The A tensor of this launch is the RAW 16-bit input (conv1: the residual stream, stored x 2^-6; conv2: conv1's
+    // output).  Each landed A box is normalised where it sits -- y = silu(v * scale[c] + shift[c]) with the same fp32
+    // arithmetic, in the same order, as the stand-alone apply pass (norm.cu), so the operand the tensor pipe sees is
+    // bit-identical -- and the separate HBM pass (read + write of the whole activation) disappears.  Thread t owns the
+    // 16-byte unit (8 channels) c_log = t & 7 of rows (t >> 3) + 16 j: its 8 (scale, shift) pairs are loaded once per
+    // stage, and the 32 lanes of a warp touch 4 whole 128-byte rows (conflict free under the 128B swizzle).  Rows of
+    // the box that lie outside the image are the convolution's zero padding (TMA zero fill) and stay untouched.
+    if constexpr (XF) {
+      const int t = (warp - 2 - C::kEpiWarps) * 32 + lane;
+      const int c_log = t & 7, r0 = t >> 3;
+      const int cpg = p.xf_cin >> 5;
+      int stage = 0; uint32_t phase = 0;
+      int cur_img = -1;
+      bool ok = true;
+      const bool chk = p.xf_check && p.fmt_a == FMT_F16;
+      __half2 mx_out = __float2half2_rn(0.f);      // range check of the normalised operand (its raw input was checked when written)
+      unsigned long long xt_wait = 0, xt_work = 0, xt_start = clock64();
+      auto hand_over = [&]() {            // the stage's A tile is final: tell the leader's MMA warp
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2 && rank != 0) mbar_arrive_cluster(smem_u32(&xf_bar[stage]), 0);
+          else mbar_arrive(smem_u32(&xf_bar[stage]));
+        }
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      };
+      for (int it = 0; ok; ++it) {
+        const int unit = unit_of(it);
+        if (unit < 0) break;
+        const TileCoord tc = tile_coord<NCTA>(p, unit, (int)rank);
+        const bool tile_ok = tc.m_tile < p.n_tiles_m;
+        if (tile_ok && tc.img != cur_img) {
+          // (scale, shift) of every input channel for this image, from the producer's fp64 sums
+          asm volatile("bar.sync 8, 128;" ::: "memory");      // nobody still reads the previous image's table
+          const double cnt = (double)p.xf_hw * cpg;
+          const double* st = p.xf_stats + (long long)tc.img * 64;
+          for (int c = t; c < p.xf_cin; c += 32 * kXfWarps) {
+            const int g = c / cpg;
+            const double m = st[g * 2] / cnt;
+            double var = st[g * 2 + 1] / cnt - m * m;
+            if (var < 0) var = 0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-6));
+            const float gr = __ldg(p.xf_gamma + c) * rstd;
+            xf_tab[c] = make_float2(gr * p.xf_in_mul, __ldg(p.xf_beta + c) - (float)m * gr);
+          }
+          asm volatile("bar.sync 8, 128;" ::: "memory");
+          cur_img = tc.img;
+        }
+        const int x_first = tc.tx * 128 - 1;                   // image column of box row 0 (left tap of a filter row)
+        for (int tap = 0; tap < p.ntaps && ok; tap += C::kGroup) {
+          const int yy = tc.ty + p.tap_o[tap][2];
+          const bool row_in = tile_ok && yy >= 0 && yy < p.Ho;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            const unsigned long long tq0 = p.dbg ? clock64() : 0;
+            ok = mbar_wait(smem_u32(&afull_bar[stage]), phase, abort_flag, p.err, 8);
+            if (!ok) break;
+            const unsigned long long tq1 = p.dbg ? clock64() : 0;
+            xt_wait += tq1 - tq0;
+            if (row_in) {
+              const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+              float sc[8], sf[8];
+              const float4* tb = reinterpret_cast<const float4*>(xf_tab + kc * kBlockK + c_log * 8);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 v = tb[q];
+                sc[2 * q] = v.x; sf[2 * q] = v.y; sc[2 * q + 1] = v.z; sf[2 * q + 1] = v.w;
+              }
+#pragma unroll 1
+              for (int jb = 0; jb < 9; jb += 3) {
+                if (p.fmt_a == FMT_F16) xf_units3<FMT_F16>(sa, r0 + 16 * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
+                else xf_units3<FMT_BF16>(sa, r0 + 16 * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
+              }
+            }
+            hand_over();
+            if (p.dbg) xt_work += clock64() - tq1;
+          }
+        }
+        for (int kc = 0; kc < p.a2_kchunks && ok; ++kc) {     // fused 1x1 branch: raw operand, nothing to normalise
+          ok = mbar_wait(smem_u32(&afull_bar[stage]), phase, abort_flag, p.err, 8);
+          if (!ok) break;
+          hand_over();
+        }
+      }
+      if (p.dbg && t == 0) {
+        p.dbg[blockIdx.x * 16 + 13] = clock64() - xt_start; p.dbg[blockIdx.x * 16 + 14] = xt_wait; p.dbg[blockIdx.x * 16 + 15] = xt_work;
+      }
+      if (chk) {
+        if (__low2float(mx_out) >= 65504.f || __high2float(mx_out) >= 65504.f) atomicCAS(p.err, 0, kErrRangeBase + SITE_GN_OUT);
+      }
     }
   } else {
     // ===================== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
@@ -1246,7 +1428,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.dbg[blockIdx.x * 16 + 5] = clock64() - t_start; p.dbg[blockIdx.x * 16 + 6] = t_tfull;
       p.dbg[blockIdx.x * 16 + 7] = t_e[0]; p.dbg[blockIdx.x * 16 + 8] = t_e[1]; p.dbg[blockIdx.x * 16 + 9] = t_e[2]; p.dbg[blockIdx.x * 16 + 10] = t_e[3];
       p.dbg[blockIdx.x * 16 + 11] = t_e[4]; p.dbg[blockIdx.x * 16 + 12] = t_e[5];
-      p.dbg[blockIdx.x * 16 + 13] = t_e[6]; p.dbg[blockIdx.x * 16 + 14] = t_e[7]; p.dbg[blockIdx.x * 16 + 15] = t_e[8];
+      if (!XF) { p.dbg[blockIdx.x * 16 + 13] = t_e[6]; p.dbg[blockIdx.x * 16 + 14] = t_e[7]; p.dbg[blockIdx.x * 16 + 15] = t_e[8]; }
     }
   }
 
@@ -1317,13 +1499,13 @@ int encode_map(CUtensorMap* m, int fmt, int rank, const void* ptr, const cuuint6
   return 0;
 }
 
-template <int BLOCK_N, int NCTA, bool HALO = false>
+template <int BLOCK_N, int NCTA, bool HALO = false, bool XF = false>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mr, const CUtensorMap& mo32,
                const CUtensorMap& mo16, const TcParams& p_in, const DevState& ds, cudaStream_t s, const char* tag) {
-  using C = Cfg<BLOCK_N, NCTA, HALO>;
+  using C = Cfg<BLOCK_N, NCTA, HALO, XF>;
   static unsigned long long attr_devs = 0;        // cudaFuncSetAttribute is per device
   if (first_use_on_device(attr_devs, ds.dev))
-    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SFV_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, NCTA, HALO, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::kSmemLimit));
   // shared-memory plan: staging rings only where this launch needs them, the rest goes to pipeline stages
   TcParams p = p_in;
@@ -1377,7 +1559,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (g_dbg) SFV_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 16 * 256, s));
-  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO>, ma, mb, ma2, mr, mo32, mo16, p));
+  SFV_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, NCTA, HALO, XF>, ma, mb, ma2, mr, mo32, mo16, p));
   SFV_LAUNCH_OK();
   if (g_dbg) {
     std::vector<unsigned long long> h(16 * 256);
@@ -1463,6 +1645,9 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   const int tiles_m_per_img = ceil_div(a.Wo, a.BW) * ceil_div(a.Ho, a.BH);
   int ncta = (g_ncta_max >= 2 && a.block_n >= 32 && (!a.b_batched || tiles_m_per_img % 2 == 0) &&
               tiles_m_per_img * a.Nimg >= 2 && !a.u8_src) ? 2 : 1;
+  const bool xf = a.xf_stats != nullptr;
+  if (xf && !(halo && a.block_n == 256 && ncta == 2 && a.a_dims[0] <= 512 && a.a_dims[0] % 32 == 0 && a.dim_y == 2))
+    return TC_NOT_FUSABLE;       // no transform variant for this launch: the caller runs the stand-alone GroupNorm pass
   {
     cuuint64_t dims[3] = {a.b_k, a.b_rows, a.b_batched ? (cuuint64_t)a.Nimg : 1};
     cuuint64_t strides[3] = {2, a.b_row_stride, a.b_batched ? a.b_batch_stride : a.b_row_stride * a.b_rows};
@@ -1526,6 +1711,8 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
                   a.block_n / a.gn_cpg <= 64,
               "tc_gemm: fused GroupNorm statistics need 4/8/16 channels per group (got %d)", a.gn_cpg);
   p.err = ds.err_flag;
+  p.xf_stats = a.xf_stats; p.xf_gamma = a.xf_gamma; p.xf_beta = a.xf_beta; p.xf_hw = (long long)a.Ho * a.Wo;
+  p.xf_cin = (int)a.a_dims[0]; p.xf_in_mul = a.xf_in_mul == 0.f ? 1.f : a.xf_in_mul; p.xf_silu = a.xf_silu; p.xf_check = a.xf_check;
   // epilogue tensor maps: per-warp boxes of 32 channels x (bx x by) pixels over the output / residual tensors
   CUtensorMap mr = ma, mo32 = ma, mo16 = ma;
   const bool tma_epi = g_epi_mode == 1 && a.block_n >= 32 && a.ldo % 8 == 0 &&
@@ -1549,6 +1736,10 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
            a.gn_stats != nullptr);
+  if (xf) {
+    snprintf(tag + strlen(tag), sizeof(tag) - strlen(tag), " xf");
+    return launch_cfg<256, 2, true, true>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
+  }
   if (halo && a.block_n == 256) return launch_cfg<256, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
   if (halo) return launch_cfg<128, 2, true>(ma, mb, ma2, mr, mo32, mo16, p, ds, s, tag);
   if (ncta == 2) {

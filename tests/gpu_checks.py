@@ -365,6 +365,37 @@ def check_encode_host_sampling(prec="fp32"):
     return out
 
 
+def check_gn_fused_transform():
+    """The opt-in fused GroupNorm path (SFV_GN_FUSE=1: transform warps normalise the raw A tile inside the HALO
+    BLOCK_N = 256 conv kernel) uses the stand-alone pass's arithmetic, so it must reproduce the default path's latents
+    bit for bit (up to the fp64 statistics atomics) -- 256x256 exercises level 1, 512x512 levels 1 and 2, a ragged
+    width the fallback for launches without the variant."""
+    out = {}
+    sd = kl_f8.init_state_dict(0)
+
+    def run(flag, u8):
+        os.environ["SFV_GN_FUSE"] = flag
+        try:
+            vae = sfv_b200.AutoencoderKL(precision="mixed")
+            vae.load_state_dict(sd)
+            p = vae.encode_uint8(u8).parameters.clone()
+            vae.check_async_error()
+            return p
+        finally:
+            os.environ.pop("SFV_GN_FUSE", None)
+
+    for B, H, W in ((2, 256, 256), (1, 512, 512), (1, 256, 392)):
+        u8 = torch.from_numpy(frames.synthetic_frames(B, H, W, 5 + W, smooth=True)).to(DEV)
+        a, b = run("1", u8), run("0", u8)
+        out[f"{B}x{H}x{W}"] = rel_l2(a, b)
+        assert out[f"{B}x{H}x{W}"] <= 1e-6, out
+    ref = kl_f8.encode(frames.normalise_u8(frames.synthetic_frames(1, 256, 256, 3, smooth=True)), sd)
+    got = run("1", torch.from_numpy(frames.synthetic_frames(1, 256, 256, 3, smooth=True)).to(DEV))
+    out["fused_vs_oracle"] = rel_l2(got[:, :4], ref.mean)
+    assert out["fused_vs_oracle"] <= 1e-2, out
+    return out
+
+
 def check_full_size_properties(prec="bf16", B=4, R=512):
     """BASELINE config-2 frame size, where the CPU oracle is too slow: size-independent
     properties -- batch permutation equivariance, determinism, finite outputs, logvar clamp range."""

@@ -168,3 +168,7 @@ def test_full_size_against_cuda_fp32_oracle(prec, R, B):
 @pytest.mark.parametrize("prec", ["fp32", "mixed"])
 def test_encode_host_posterior_sampling(prec):
     print(_c().check_encode_host_sampling(prec))
+
+
+def test_fused_groupnorm_transform_matches_default_path():
+    print(_c().check_gn_fused_transform())

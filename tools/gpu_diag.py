@@ -71,6 +71,7 @@ def plan():
               ("fullsize_oracle/bf16/512", "check_full_size_oracle('bf16',512,4)"),
               ("precompute/mixed", "check_precompute_driver('mixed')"), ("precompute/fp32", "check_precompute_driver('fp32')"),
               ("dataset/device", "check_resident_dataset()"),
+              ("gn_fused", "check_gn_fused_transform()"),
               ("sampling/fp32", "check_encode_host_sampling('fp32')"), ("sampling/mixed", "check_encode_host_sampling('mixed')")]
     return items
 
