@@ -514,7 +514,8 @@ __device__ __forceinline__ void conv_in_store_rows(const float (&v)[3][18], uint
   }
 }
 
-constexpr int kXfWarps = 4;             // transform warps of an XF kernel
+constexpr int kXfWarps = 8;             // transform warps of an XF kernel (two per scheduler: the transform is MUFU / latency bound)
+constexpr int kXfRowStep = 4 * kXfWarps; // rows of the A box covered by one pass of all transform threads (8 units per row)
 template <int BLOCK_N, int NCTA, bool HALO = false, bool XF = false>
 struct Cfg {
   static constexpr int kGroup = HALO ? 3 : 1;                           // filter taps per pipeline stage
@@ -561,11 +562,12 @@ __device__ __forceinline__ float xf_silu_tanh(float t) {      // t * sigmoid(t) 
 template <int FMT>
 __device__ __forceinline__ void xf_units3(uint32_t sa, int r_first, int c_log, int x_first, int Wo, const float (&sc)[8],
                                           const float (&sf)[8], bool silu, bool chk, __half2& mx_out) {
+  constexpr int kStep = kXfRowStep;
   uint32_t w[3][4];
   bool on[3];
 #pragma unroll
   for (int u = 0; u < 3; ++u) {
-    const int r = r_first + 16 * u;
+    const int r = r_first + kStep * u;
     const int px = x_first + r;
     on[u] = r < 130 && px >= 0 && px < Wo;
     if (on[u]) {
@@ -594,7 +596,7 @@ __device__ __forceinline__ void xf_units3(uint32_t sa, int r_first, int c_log, i
   }
 #pragma unroll
   for (int u = 0; u < 3; ++u) {
-    const int r = r_first + 16 * u;
+    const int r = r_first + kStep * u;
     if (on[u]) sts128u(sa + r * 128 + ((c_log ^ (r & 7)) << 4), w[u][0], w[u][1], w[u][2], w[u][3]);
   }
 }
@@ -919,7 +921,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool tile_ok = tc.m_tile < p.n_tiles_m;
         if (tile_ok && tc.img != cur_img) {
           // (scale, shift) of every input channel for this image, from the producer's fp64 sums
-          asm volatile("bar.sync 8, 128;" ::: "memory");      // nobody still reads the previous image's table
+          asm volatile("bar.sync 8, %0;" ::"n"(32 * kXfWarps) : "memory");      // nobody still reads the previous image's table
           const double cnt = (double)p.xf_hw * cpg;
           const double* st = p.xf_stats + (long long)tc.img * 64;
           for (int c = t; c < p.xf_cin; c += 32 * kXfWarps) {
@@ -931,7 +933,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float gr = __ldg(p.xf_gamma + c) * rstd;
             xf_tab[c] = make_float2(gr * p.xf_in_mul, __ldg(p.xf_beta + c) - (float)m * gr);
           }
-          asm volatile("bar.sync 8, 128;" ::: "memory");
+          asm volatile("bar.sync 8, %0;" ::"n"(32 * kXfWarps) : "memory");
           cur_img = tc.img;
         }
         const int x_first = tc.tx * 128 - 1;                   // image column of box row 0 (left tap of a filter row)
@@ -954,9 +956,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 sc[2 * q] = v.x; sf[2 * q] = v.y; sc[2 * q + 1] = v.z; sf[2 * q + 1] = v.w;
               }
 #pragma unroll 1
-              for (int jb = 0; jb < 9; jb += 3) {
-                if (p.fmt_a == FMT_F16) xf_units3<FMT_F16>(sa, r0 + 16 * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
-                else xf_units3<FMT_BF16>(sa, r0 + 16 * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
+              for (int jb = 0; jb * kXfRowStep < 130; jb += 3) {
+                if (p.fmt_a == FMT_F16) xf_units3<FMT_F16>(sa, r0 + kXfRowStep * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
+                else xf_units3<FMT_BF16>(sa, r0 + kXfRowStep * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
               }
             }
             hand_over();
