@@ -152,6 +152,9 @@ def test_mixed_mode_never_saturates_silently():
 
 @pytest.mark.parametrize("prec", ["mixed", "fp32"])
 def test_precompute_driver_video_to_reference_npy(prec):
+    from oracle import ref_shim
+    if ref_shim.video_path() is None:
+        pytest.skip("the reference's sample video is not present (oracle/_ref/videos, placed by __graft_entry__.build())")
     print(_c().check_precompute_driver(prec))
 
 
