@@ -556,28 +556,29 @@ __device__ __forceinline__ float xf_silu_tanh(float t) {      // t * sigmoid(t) 
   return fmaf(h, th, h);
 }
 
-// Three of a transform thread's 16-byte units (rows r, r + 16, r + 32 of the A box): loads back to back, arithmetic with
-// all 24 values independent, stores.  Kept a compact, rolled-loop body on purpose: the fully unrolled nine-unit version
-// is ~1000 straight-line instructions per stage and ran instruction-fetch bound (2850 cycles per stage measured).
+// One stage of a transform thread: its 16-byte units (8 channels c_log*8.. of rows r0, r0 + 32, r0 + 64, r0 + 96, and for
+// the 16 threads with r0 < 2 also r0 + 128) are all loaded first, then normalised with every value independent, then
+// stored.  Straight-line code of ~200 instructions: a per-unit load / compute / store loop serialised on the LDS and
+// MUFU latencies (ncu: the first use of the loaded word was the top stall), the nine-unit unrolled form of the
+// four-warp version was instruction-fetch bound.  Columns outside the image (the convolution's zero padding, filled
+// by TMA) are computed but never written back.
 template <int FMT>
-__device__ __forceinline__ void xf_units3(uint32_t sa, int r_first, int c_log, int x_first, int Wo, const float (&sc)[8],
-                                          const float (&sf)[8], bool silu, bool chk, __half2& mx_out) {
-  constexpr int kStep = kXfRowStep;
-  uint32_t w[3][4];
-  bool on[3];
+__device__ __forceinline__ void xf_stage(uint32_t sa, int r0, int c_log, int x_first, int Wo, const float (&sc)[8],
+                                         const float (&sf)[8], bool silu, bool chk, __half2& mx_out) {
+  constexpr int kMain = 128 / kXfRowStep;              // units every thread owns (rows < 128)
+  uint32_t w[kMain + 1][4];
+  const bool tail = r0 + kMain * kXfRowStep < 130;     // rows 128, 129
 #pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int r = r_first + kStep * u;
-    const int px = x_first + r;
-    on[u] = r < 130 && px >= 0 && px < Wo;
-    if (on[u]) {
+  for (int u = 0; u <= kMain; ++u) {
+    const int r = r0 + kXfRowStep * u;
+    if (u < kMain || tail) {
       const float4 q = lds128(sa + r * 128 + ((c_log ^ (r & 7)) << 4));
       w[u][0] = __float_as_uint(q.x); w[u][1] = __float_as_uint(q.y); w[u][2] = __float_as_uint(q.z); w[u][3] = __float_as_uint(q.w);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    if (on[u]) {
+  for (int u = 0; u <= kMain; ++u) {
+    if (u < kMain || tail) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float a, b;
@@ -586,18 +587,21 @@ __device__ __forceinline__ void xf_units3(uint32_t sa, int r_first, int c_log, i
         if (silu) { a = xf_silu_tanh(a); b = xf_silu_tanh(b); }
         w[u][i] = pack2_16(a, b, FMT);
       }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u <= kMain; ++u) {
+    const int r = r0 + kXfRowStep * u;
+    const int px = x_first + r;
+    if ((u < kMain || tail) && px >= 0 && px < Wo) {
       if (FMT == FMT_F16 && chk) {
         mx_out = __hmax2(__hmax2(mx_out, __habs2(*reinterpret_cast<const __half2*>(&w[u][0]))),
                          __habs2(*reinterpret_cast<const __half2*>(&w[u][1])));
         mx_out = __hmax2(__hmax2(mx_out, __habs2(*reinterpret_cast<const __half2*>(&w[u][2]))),
                          __habs2(*reinterpret_cast<const __half2*>(&w[u][3])));
       }
+      sts128u(sa + r * 128 + ((c_log ^ (r & 7)) << 4), w[u][0], w[u][1], w[u][2], w[u][3]);
     }
-  }
-#pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int r = r_first + kStep * u;
-    if (on[u]) sts128u(sa + r * 128 + ((c_log ^ (r & 7)) << 4), w[u][0], w[u][1], w[u][2], w[u][3]);
   }
 }
 
@@ -955,11 +959,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 v = tb[q];
                 sc[2 * q] = v.x; sf[2 * q] = v.y; sc[2 * q + 1] = v.z; sf[2 * q + 1] = v.w;
               }
-#pragma unroll 1
-              for (int jb = 0; jb * kXfRowStep < 130; jb += 3) {
-                if (p.fmt_a == FMT_F16) xf_units3<FMT_F16>(sa, r0 + kXfRowStep * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
-                else xf_units3<FMT_BF16>(sa, r0 + kXfRowStep * jb, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
-              }
+              if (p.fmt_a == FMT_F16) xf_stage<FMT_F16>(sa, r0, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
+              else xf_stage<FMT_BF16>(sa, r0, c_log, x_first, p.Wo, sc, sf, p.xf_silu != 0, chk, mx_out);
             }
             hand_over();
             if (p.dbg) xt_work += clock64() - tq1;
