@@ -87,6 +87,8 @@ struct TcParams {
   int relu;
   double* gn_stats; int gn_cpg; int gn_groups;   // fused GroupNorm partial sums: channels per group, groups
   int epi_mode;
+  int epi_fast;                        // lean epilogue of the level-0 launches is applicable (host-side conditions)
+  int res_inplace;                     // lean epilogue: the output tile is built in the residual's ring slot and stored from there
   int halo_base_offset;
   int num_stages, res_bufs, h16_slots;   // shared-memory plan of this launch
   int res_prefetch;                    // L2-prefetch the residual one tile ahead of its TMA load
@@ -1047,6 +1049,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kNChunk = kColsPerSet / C::kChunk;      // chunks of 32 columns this warp handles per tile
     const bool use_tma = C::kChunk == 32 && p.epi_mode == 1;
     const bool has_res = p.residual != nullptr;
+    const bool epi_fast = p.epi_fast && use_tma && (has_res ? kResBufs >= 2 && (p.res_inplace || p.h16_slots == 2) : p.h16_slots == 2);
     // ---- residual prefetch stream (TMA): global chunk index g = tile_seq * kNChunk + c -> ring slot g % kResBufs
     uint8_t* f32_w = epi_f32 + ew * (kResBufs * kResSlot);
     const uint32_t f32_s = smem_u32(f32_w), bias_s = smem_u32(bias_w);
@@ -1107,6 +1110,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!ok) break;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      bool handed_back = false;                // the lean path returns the accumulator stage before its math
       if constexpr (C::kChunk == 32) {
         if (use_tma) {
           // ---- asynchronous, coalesced epilogue: residual in by TMA (prefetched kResBufs-1 chunks ahead),
@@ -1193,6 +1197,116 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (c + 2 < kNChunk) tmem_ld32(t_row + cbase + (c + 2) * 32, va);
                 chunk(vb, c + 1);
               }
+            }
+          } else if (kRegStats && epi_fast) {
+            if constexpr (kRegStats) {
+              // ---- lean path of the level-0 launches (128-wide tiles, two 32-column chunks per warp, fp16 stream or
+              //      conv1 output, 4 channels per group, optional 16-bit residual; whole tiles only): the same arithmetic
+              //      as the general loop below with formats and options fixed at compile time.  Both TMEM loads are in
+              //      flight together and the accumulator stage goes back to the MMA warp before the math starts.
+              uint32_t va[32], vb[32];
+              tmem_ld32(t_row + cbase, va);
+              tmem_ld32(t_row + cbase + 32, vb);
+              unsigned long long tq = kFineDbg && p.dbg ? clock64() : 0;
+              tmem_ld_wait();
+              if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[1] += t1 - tq; tq = t1; }
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (NCTA == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
+                else mbar_arrive(smem_u32(&tempty_bar[acc]));
+              }
+              handed_back = true;
+              const int ox = tx * p.BW + wx, oy = ty * p.BH + wy;
+              const int colw = n_tile * BLOCK_N + cbase;
+              const float alpha = p.alpha;
+              // three-slot ring: the residual chunks to prefetch while this tile is processed are the same two column
+              // chunks of this CTA's NEXT tile -> its coordinates are computed once per tile
+              const bool ring3 = has_res && kResBufs == 3;
+              bool nvalid = false; int ncol = 0, nox = 0, noy = 0, nimg = 0;
+              if (ring3 && unit + unit_step < p.n_units) {
+                const TileCoord tn = tile_coord<NCTA>(p, unit + unit_step, (int)rank);
+                nvalid = true; ncol = tn.n_tile * BLOCK_N + cbase; nox = tn.tx * p.BW + wx; noy = tn.ty * p.BH + wy; nimg = tn.img;
+              }
+              auto fast_chunk = [&](const uint32_t (&v)[32], const int c) -> bool {
+                const int slot = rslot;
+                const uint32_t bw = bias_s + c * 128;
+                float f[32];
+                if (kFineDbg && p.dbg) tq = clock64();
+                if (has_res) {
+                  if (!mbar_wait(smem_u32(&res_bar_w[slot]), rphase, abort_flag, p.err, 5)) return false;
+                  if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[0] += t1 - tq; tq = t1; }
+                  const uint32_t rb = f32_s + slot * kResSlot + lane * 64;
+                  const float rm = p.res_mul;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 q = lds128(rb + ((j ^ sw16) << 4));
+                    const float4 b0 = lds128(bw + j * 32), b1 = lds128(bw + j * 32 + 16);
+                    float r8[8];
+                    unpack2_16(__float_as_uint(q.x), FMT_F16, r8[0], r8[1]); unpack2_16(__float_as_uint(q.y), FMT_F16, r8[2], r8[3]);
+                    unpack2_16(__float_as_uint(q.z), FMT_F16, r8[4], r8[5]); unpack2_16(__float_as_uint(q.w), FMT_F16, r8[6], r8[7]);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[8 * j + i] = fmaf(r8[i], rm, fmaf(__uint_as_float(v[8 * j + i]), alpha, bb[i]));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = lds128(bw + j * 16);
+                    f[4 * j] = fmaf(__uint_as_float(v[4 * j]), alpha, b4.x);
+                    f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b4.y);
+                    f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b4.z);
+                    f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b4.w);
+                  }
+                }
+                if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[6] += t1 - tq; tq = t1; }
+                epi_stats_lane<4>(f, row_ok, gacc + c * 16);
+                if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[7] += t1 - tq; tq = t1; }
+                // staging tile of the store: with a residual, the ring slot the residual arrived in (same 32 x 64 B
+                // swizzled layout; every lane overwrites exactly the 64 bytes it has just read), which leaves the
+                // shared memory of the separate output tiles to a fourth pipeline stage
+                const uint32_t ht = (has_res && p.res_inplace) ? f32_s + slot * kResSlot : h16_s + (g_cur & 1) * 2048;
+                const uint32_t hb = ht + lane * 64;
+                __half2 mx = __float2half2_rn(0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t w0 = pack2_16(f[8 * j], f[8 * j + 1], FMT_F16), w1 = pack2_16(f[8 * j + 2], f[8 * j + 3], FMT_F16);
+                  const uint32_t w2 = pack2_16(f[8 * j + 4], f[8 * j + 5], FMT_F16), w3 = pack2_16(f[8 * j + 6], f[8 * j + 7], FMT_F16);
+                  mx = __hmax2(__hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w0))), __habs2(*reinterpret_cast<const __half2*>(&w1)));
+                  mx = __hmax2(__hmax2(mx, __habs2(*reinterpret_cast<const __half2*>(&w2))), __habs2(*reinterpret_cast<const __half2*>(&w3)));
+                  sts128u(hb + ((j ^ sw16) << 4), w0, w1, w2, w3);
+                }
+                if (p.sat_check && row_ok && (__low2float(mx) >= 65504.f || __high2float(mx) >= 65504.f))
+                  atomicCAS(p.err, 0, kErrRangeBase + SITE_XCOPY);
+                if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[8] += t1 - tq; tq = t1; }
+                fence_proxy_async();
+                __syncwarp();
+                if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[2] += t1 - tq; tq = t1; }
+                if (elect_one_sync()) {
+                  tma_store_4d(&tmO16, ht, colw + c * 32, ox, oy, img);
+                  tma_store_commit();
+                  tma_store_wait_read<1>();                      // the previous chunk's staging tile is free again
+                }
+                __syncwarp();
+                if (kFineDbg && p.dbg) { const unsigned long long t1 = clock64(); t_e[3] += t1 - tq; tq = t1; }
+                if (ring3) {                                     // refill the slot freed by the wait above
+                  if (nvalid && elect_one_sync()) {
+                    const int fs = slot == 0 ? 2 : slot - 1;
+                    const uint32_t bar = smem_u32(&res_bar_w[fs]);
+                    mbar_arrive_expect_tx(bar, (uint32_t)kResSlot);
+                    tma_load_4d(f32_s + fs * kResSlot, &tmR, bar, ncol + c * 32, nox, noy, nimg);
+                  }
+                  __syncwarp();
+                } else if (has_res) {
+                  issue_residual(g_cur + kResBufs - 1, slot == 0 ? kResBufs - 1 : slot - 1);
+                }
+                ++g_cur;
+                rslot = (rslot + 1 == kResBufs) ? 0 : rslot + 1;
+                rphase ^= (rslot == 0);
+                return true;
+              };
+              ok = fast_chunk(va, 0) && fast_chunk(vb, 1);
+              if (!ok) break;
             }
           } else
 #pragma unroll (kRegStats ? 2 : 1)
@@ -1413,11 +1527,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
       const unsigned long long t_end0 = p.dbg ? clock64() : 0;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (NCTA == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);   // the leader's MMA thread waits
-        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (!handed_back) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (NCTA == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);   // the leader's MMA thread waits
+          else mbar_arrive(smem_u32(&tempty_bar[acc]));
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (p.dbg) t_e[5] += clock64() - t_end0;
@@ -1460,6 +1576,7 @@ int g_res_prefetch = 0;  // SFV_RES_PREFETCH=1: L2-prefetch residual chunks one 
 int g_halo_boff = 0;    // descriptor base-offset for the shifted taps: measured WRONG on B200 (the swizzle is a function of
                         // the absolute smem address bits), so it stays 0; SFV_HALO_BOFF=1 reproduces the failing variant
 int g_epi_mode = 1;
+int g_epi_fast = 1;     // SFV_EPI_FAST=0: level-0 launches take the general epilogue loop; 2: lean loop with separate output tiles (A/B)
 unsigned long long* g_dbg = nullptr;   // SFV_TC_DEBUG=1: per-CTA role cycle counters, printed after each launch (synchronous)     // SFV_EPI=0: write rows straight from registers; 1: coalesced via smem transpose
 
 int tc_init() {
@@ -1471,6 +1588,7 @@ int tc_init() {
     return fail(SFV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (const char* e = getenv("SFV_NCTA")) g_ncta_max = atoi(e);
   if (const char* e = getenv("SFV_EPI")) g_epi_mode = atoi(e);
+  if (const char* e = getenv("SFV_EPI_FAST")) g_epi_fast = atoi(e);
   if (const char* e = getenv("SFV_HALO")) g_halo = atoi(e);
   if (const char* e = getenv("SFV_HALO_BOFF")) g_halo_boff = atoi(e);
   if (const char* e = getenv("SFV_RES_PREFETCH")) g_res_prefetch = atoi(e);
@@ -1544,6 +1662,12 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     }
     if (g_epi_slots_r >= 0 && need_f32) p.res_bufs = g_epi_slots_r;       // SFV_EPI_SLOTS=r,h experiment override
     if (g_epi_slots_h >= 0 && need_h16) p.h16_slots = g_epi_slots_h;
+  }
+  p.res_inplace = 0;
+  if (p.epi_fast && p.res16 && C::kSets == 2 && BLOCK_N == 128 && g_epi_fast != 2 && g_epi_slots_r < 0 && g_epi_slots_h < 0) {
+    // lean level-0 epilogue with a 16-bit residual: three ring slots per warp serve the residual load, the math and
+    // the store of consecutive chunks; no separate output tiles
+    p.res_inplace = 1; p.res_bufs = 3; p.h16_slots = 0;
   }
   p.num_stages = C::stages_for(p.res_bufs, p.h16_slots, p.res_slot);
   SFV_CHECK(p.num_stages >= (HALO ? 2 : 3), "tc_gemm: pipeline too shallow (%d stages)", p.num_stages);
@@ -1735,6 +1859,9 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
     if (a.out_f32) SFV_TRY(encode_map(&mo32, a.fmt, 4, a.out_f32, dims, st32, box, 128, true));
     if (a.out_16) SFV_TRY(encode_map(&mo16, fmt_out, 4, a.out_16, dims, st16, box, 64, false));
   }
+  p.epi_fast = g_epi_fast && tma_epi && !a.softmax_mode && a.block_n == 128 && a.out_16 && !a.out_f32 && p.out16_scale == 1.f &&
+               fmt_out == FMT_F16 && !a.relu && a.gn_stats && a.gn_cpg == 4 && (!a.residual || p.res16) &&
+               a.Cout % a.block_n == 0 && p.n_tiles_m % ncta == 0;
   char tag[64];
   snprintf(tag, sizeof(tag), "M=%dx%dx%d N=%d K=%dx%d bn=%d cta=%d%s res=%d f32=%d o16=%d gn=%d", a.Nimg, a.Ho, a.Wo, a.Cout,
            a.ntaps, a.kchunks * 64, a.block_n, ncta, halo ? "h" : "", a.residual != nullptr, a.out_f32 != nullptr, a.out_16 != nullptr,
