@@ -13,7 +13,8 @@ encoder -> bit-packed code (latent_dim 25, noise_ratio 0).
                  CUDA-event launch durations, against MEASURED_PEAKS.json
   cpu_baseline : the UNMODIFIED reference modules (oracle/_ref, placed there by
                  oracle/build_ref.py) on the host cores, on a bounded sample; the
-                 oracle port is checked against them in the same run
+                 oracle port is checked against them in the same run (N = 1 only;
+                 at N > 1 cpu_baseline and parity are null)
 N > 1 (torchrun, one rank per GPU): each rank encodes its own contiguous range of
 64 frames (weak scaling, no data-path collective); its kernels write latents, codes
 and h straight into its block of double-buffered gather buffers, and one in-place
@@ -524,7 +525,7 @@ def main():
     cpu = None
     parity = None
     ref = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # the CPU leg (and the parity it anchors) belongs to the N=1 run only
         cores = host_threads()
         n_cpu = PARITY_FRAMES if res <= 512 else 2
         u8 = host[0][:n_cpu].numpy()
