@@ -24,7 +24,7 @@ def main(path, tag):
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     out = [f"# ncu --set full --clock-control none ({tag}): every tcgen05 / GroupNorm / conv_in / softmax launch of one",
-           "# 8-frame 512x512 chunk (tools/profile_step.py, bf16 operands).  Per-launch times are cold-cache and",
+           "# 8-frame 512x512 chunk (tools/profile_step.py mixed 8: mixed operand mode, 16-bit residual stream).  Per-launch times are cold-cache and",
            "# serialised under the profiler: use the shares and the per-launch traffic, not the absolute times.", "",
            "| # | kernel | " + " | ".join(n for n, _ in WANT) + " |", "|---|---|" + "---:|" * len(WANT)]
     agg = {}
