@@ -336,8 +336,7 @@ int conv_tc(const ConvW& w, TcFmt fmt, const void* in16, int N, int H, int W, in
     a.xf_check = xf->check;
   }
   a.out_f32 = out_f32; a.out_16 = out_16; a.ldo = w.Cout; a.relu = relu;
-  if (gn_stats) {   // fused GroupNorm(32) statistics of the output; accumulators must start at zero
-    SFV_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 2 * 32 * N, s));
+  if (gn_stats) {   // fused GroupNorm(32) statistics of the output; the CALLER zeroed the accumulators
     a.gn_stats = gn_stats; a.gn_cpg = w.Cout / 32;
   }
   return launch_tc_gemm(a, s);
@@ -388,10 +387,12 @@ static const bool g_attn_fused = []() { const char* e = getenv("SFV_ATTN_FUSED")
 
 namespace {
 
+constexpr int kStatSlots = 40;     // conv_in + 2 per ResnetBlock (10) + nin / Downsample / proj_out launches (<= 28), with slack
+
 struct Plan {
   void *xa, *xb;            // residual stream ping-pong: fp32, or (stream16) 16-bit scaled
   void *oa, *ob, *x16, *x16b;
-  double* stats; double* stats2;
+  double* stats; double* stat_slots; int stat_stride;   // check-mode statistics; per-launch slots of fused statistics
   float* S; void* P; float* moments;
   int attn_chunk;
 };
@@ -410,7 +411,9 @@ void make_plan(bool tc, bool s16, int Bc, int H, int W, Arena& ar, Plan* p) {
   p->x16 = tc ? ar.take(s16 ? (size_t)Bc * 512 * Lp0 * 2 : E0 * osz) : nullptr;
   p->x16b = (tc && !s16) ? ar.take(E0 / 4 * osz) : nullptr;
   p->stats = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
-  p->stats2 = (double*)ar.take(sizeof(double) * 2 * 32 * Bc);
+  // fused GroupNorm statistics: every producing launch of a forward gets its own slot, all zeroed by one memset
+  p->stat_stride = 2 * 32 * Bc;
+  p->stat_slots = (double*)ar.take(sizeof(double) * p->stat_stride * kStatSlots);
   const size_t Lp = (L + 7) / 8 * 8;                  // row pitch of S / P / V^T (16-byte rows for TMA)
   // the fp32 score matrix S exists only in the check mode and in the unfused A/B path; the tensor-core path keeps the
   // scores on chip and stores P (16 bit) only
@@ -453,9 +456,9 @@ struct Fwd {
     const float xs = e->xc_scale;
     if (!tc) return conv_f32(w, in_op, SRC_NHWC_F32, N, H, W, stride, pad_lo, pad_hi, (const float*)res, (float*)xo, 0, 1.f, s);
     if (s16)
-      return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, nullptr, xo, 0, s, sx(), a2, in_scale, xs,
+      return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, nullptr, xo, 0, s, nsx(), a2, in_scale, xs,
                      res != nullptr, 1.f / xs, 0, xf);
-    return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, (float*)xo, copy, 0, s, sx(), a2, in_scale, xs);
+    return conv_tc(w, cf(), in_op, N, H, W, stride, pad_lo, pad_hi, res, (float*)xo, copy, 0, s, nsx(), a2, in_scale, xs);
   }
   // formats of a conv whose A operand is a GroupNorm / conv1 output (fmt) and whose 16-bit output is one too
   TcFmt cf() const { return TcFmt{fmt, e->fmt_w, fmt}; }
@@ -473,8 +476,17 @@ struct Fwd {
   }
   // statistics buffers: sx holds the stats of the current stream x (written by whichever kernel
   // produced x), sh those of conv1's output; both null in check mode.
-  double* sx() { return (tc && e->fused_stats) ? pl.stats2 : nullptr; }
-  double* sh() { return (tc && e->fused_stats) ? pl.stats : nullptr; }
+  // A producer takes a fresh, already zeroed slot (nsx / nsh); consumers read the current one (sx / sh).
+  double* sx_p = nullptr; double* sh_p = nullptr; int stat_slot = 0;
+  double* take_slot() {
+    if (!(tc && e->fused_stats)) return nullptr;
+    if (stat_slot >= kStatSlots) return nullptr;          // (cannot happen with this graph) the consumer then runs its own statistics pass
+    return pl.stat_slots + (size_t)(stat_slot++) * pl.stat_stride;
+  }
+  double* nsx() { return sx_p = take_slot(); }
+  double* nsh() { return sh_p = take_slot(); }
+  double* sx() const { return sx_p; }
+  double* sh() const { return sh_p; }
 
   // x: residual stream (C=Cin), x_op: 16-bit operand copy of x (needed only when r.has_nin; == x with a 16-bit stream).
   // Writes the block output to `xo` (and, fp32 stream only, its operand copy to pl.x16 if want_copy).
@@ -486,19 +498,20 @@ struct Fwd {
     // elsewhere the stand-alone apply pass writes the operand first.
     const bool fuse = s16 && e->gn_fuse && e->fused_stats;
     XfIn xf1{sx(), r.n1.gamma, r.n1.beta, 1.f / e->xc_scale, 1, e->range_check ? 1 : 0};
-    XfIn xf2{sh(), r.n2.gamma, r.n2.beta, 1.f, 1, e->range_check ? 1 : 0};
     // (with fusion on, conv1's epilogue range-checks h as it stores it: the stand-alone apply pass that used to read h
     // and check it may not run)
     const int chk_h = (fuse && e->range_check) ? 1 : 0;
-    int st = fuse ? conv_tc(r.c1, cf(), x, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, sh(), nullptr, 1.f, 1.f, 0, 1.f, chk_h, &xf1)
+    double* const h_stats = nsh();             // conv1's epilogue accumulates the statistics of h here
+    int st = fuse ? conv_tc(r.c1, cf(), x, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, h_stats, nullptr, 1.f, 1.f, 0, 1.f, chk_h, &xf1)
                   : TC_NOT_FUSABLE;
     if (st == TC_NOT_FUSABLE) {
       SFV_TRY(gn_x(r.n1, x, HW, 1, pl.oa));
-      if (tc) SFV_TRY(conv_tc(r.c1, cf(), pl.oa, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, sh(), nullptr, 1.f, 1.f, 0, 1.f, chk_h));
-      else SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, sh()));
+      if (tc) SFV_TRY(conv_tc(r.c1, cf(), pl.oa, N, H, W, 1, 1, 1, nullptr, nullptr, pl.ob, 0, s, h_stats, nullptr, 1.f, 1.f, 0, 1.f, chk_h));
+      else SFV_TRY(conv(r.c1, pl.oa, H, W, 1, nullptr, nullptr, pl.ob, h_stats));
     } else if (st != 0) {
       return st;
     }
+    XfIn xf2{sh(), r.n2.gamma, r.n2.beta, 1.f, 1, e->range_check ? 1 : 0};
     const void* res = x;
     void* copy = (tc && want_copy && !s16) ? pl.x16 : nullptr;
     const float xs = e->xc_scale;              // the 16-bit copies of x (or x itself) hold xs * x
@@ -545,10 +558,10 @@ struct Fwd {
                              scale, s));
       }
       if (s16)
-        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, nullptr, xo, 0, s, sx(), nullptr, 1.f,
+        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, nullptr, xo, 0, s, nsx(), nullptr, 1.f,
                         e->xc_scale, 1, 1.f / e->xc_scale));
       else
-        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, (float*)xo, nullptr, 0, s, sx()));
+        SFV_TRY(conv_tc(e->proj, TcFmt{fa, fa, fmt}, O, N, h, w, 1, 0, 0, x, (float*)xo, nullptr, 0, s, nsx()));
     } else {
       float* q = (float*)pl.ob;
       float* k = q + (size_t)N * L * C;
@@ -692,12 +705,14 @@ int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, in
     };
     // conv_in straight from the boundary layout (fp32 NCHW or uint8 HWC)
     const char* xin = (const char*)x + (size_t)b0 * 3 * H * W * (src_kind == SRC_NHWC_U8 ? 1 : 4);
-    if (f.sx()) SFV_CUDA(cudaMemsetAsync(f.sx(), 0, sizeof(double) * 2 * 32 * N, s));
+    if (tc && e->fused_stats)       // every statistics slot of this forward, once
+      SFV_CUDA(cudaMemsetAsync(f.pl.stat_slots, 0, sizeof(double) * f.pl.stat_stride * kStatSlots, s));
+    double* const st_in = f.nsx();
     if (tc && src_kind == SRC_NHWC_U8 && e->conv_in.w16_u8 && e->conv_in_tc && W % 8 == 0 && ((uintptr_t)xin & 3) == 0)
-      SFV_TRY(conv_in_tc(e->conv_in, e->fmt_w, (const unsigned char*)xin, N, H, W, s16 ? nullptr : (float*)f.pl.xa, f.sx(), s,
+      SFV_TRY(conv_in_tc(e->conv_in, e->fmt_w, (const unsigned char*)xin, N, H, W, s16 ? nullptr : (float*)f.pl.xa, st_in, s,
                          s16 ? f.pl.xa : nullptr, e->fmt, e->xc_scale));
     else
-      SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, (float*)f.pl.xa, f.sx(), N, H, W, s,
+      SFV_TRY(launch_conv_in(xin, src_kind, e->conv_in.w32, e->conv_in.bias, (float*)f.pl.xa, st_in, N, H, W, s,
                              s16 ? f.pl.xa : nullptr, e->fmt, e->xc_scale));
     SFV_TRY(tap(0, f.pl.xa, H, W));
     void* cur = f.pl.xa; void* oth = f.pl.xb;
