@@ -67,6 +67,7 @@ typedef struct SfvTensor {
 
 typedef struct SfvEncoder SfvEncoder;   /* AutoencoderKL.encoder + quant_conv */
 typedef struct SfvRbvae SfvRbvae;       /* Seq2SeqBinaryVAE encoder half       */
+typedef struct SfvRbvaeDecoder SfvRbvaeDecoder;   /* decoder_rnn + ConvDecoder (training-side forward) */
 
 const char* sfv_version(void);
 const char* sfv_last_error(void);
@@ -176,6 +177,39 @@ int sfv_rbvae_encode(SfvRbvae* rb, const float* x, int32_t B, int32_t T, float i
                      const float* u_or_null, float noise_ratio, float temperature, int32_t hard,
                      float* h_out, float* z_out, uint32_t* codes_out,
                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- decoder half and losses: the training-side forward, fp32, forward values only -------------
+ * Replaces DecoderRNN.forward + ConvDecoder.forward, i.e. the second half of Seq2SeqBinaryVAE.forward
+ * (models/percep_RBVAE/percep_RBVAE_model.py:71-91,110-122,159-168;
+ *  models/contrastive_RBVAE/contrastive_RBVAE_model.py:70-90,109-121).  Tensors: the reference keys
+ * decoder_cnn.fc.{weight,bias}, decoder_cnn.deconv.{0,3,6}.{weight,bias} (ConvTranspose2d layout [Cin,Cout,3,3]),
+ * decoder_rnn.lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l{k}.  out_h x out_w is the reconstruction's size
+ * (a multiple of 8; fc.out_features must equal channels * out_h/8 * out_w/8 -- the reference hard-wires 11x20). */
+int sfv_rbvae_decoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t out_channels, int32_t out_h,
+                             int32_t out_w, SfvRbvaeDecoder** out);
+void sfv_rbvae_decoder_destroy(SfvRbvaeDecoder* d);
+int sfv_rbvae_decoder_workspace_bytes(const SfvRbvaeDecoder* d, int32_t N, size_t* bytes);
+/*  z_seq    fp32 [B,T,L]  binary-concrete output of the encoder half
+ *  d_seq_out fp32 [B,T,L] decoder LSTM output, or NULL
+ *  x_recon  fp32 [B,T,C,out_h,out_w] (NCHW per frame), values in (0,1) */
+int sfv_rbvae_decode(SfvRbvaeDecoder* d, const float* z_seq, int32_t B, int32_t T, float* d_seq_out, float* x_recon,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Losses of models/percep_RBVAE/percep_RBVAE_train.py:27-107 (the contrastive trainer uses the same functions).
+ * Every result is ONE fp32 value written to device memory `out`.
+ *  sfv_loss_mse       recon_loss = F.mse_loss(a, b)                                    (:32-33)
+ *  sfv_loss_l1        l1_loss = lamb * torch.norm(q, p=1)                              (:27-29)
+ *  sfv_loss_kl_binary_concrete  KL(Bernoulli(sigmoid(q)) || Bernoulli(p)), summed over the L latents, mean over rows (:52-77)
+ *  sfv_loss_contrast  contrast_loss(x1, x2, label, margin, dist): cosine != 0 -> 1 - cosine_similarity, else
+ *                     F.pairwise_distance                                              (:80-107)
+ *  sfv_loss_triplet   F.triplet_margin_loss(a, p, n, margin, p=2, eps, swap, 'mean')   (:35-49) */
+int sfv_loss_mse(const float* a, const float* b, int64_t n, float* out, void* stream);
+int sfv_loss_l1(const float* q, int64_t n, float lamb, float* out, void* stream);
+int sfv_loss_kl_binary_concrete(const float* q_logits, int64_t rows, int32_t L, float p, float eps, float* out, void* stream);
+int sfv_loss_contrast(const float* x1, const float* x2, const float* label, int32_t rows, int32_t D, float margin,
+                      int32_t cosine, float* out, void* stream);
+int sfv_loss_triplet(const float* anchor, const float* pos, const float* neg, int32_t rows, int32_t D, float margin,
+                     float eps, int32_t swap, float* out, void* stream);
 
 /* Hamming distance matrix between packed codes (evaluation helper for
  * scripts/evaluation/clustering_eval/embedding_hamming_distance.py:53-87):

@@ -73,6 +73,51 @@ def rbvae_case(name, kind, cin, ch, layers, L, hw, seed, T):
     print(name, "min|h|", float(h_seq.abs().min()), "max|h|", float(h_seq.abs().max()))
 
 
+def rbvae_forward_case(name, kind, cin, ch, layers, L, hw, seed, B, T):
+    """Full Seq2SeqBinaryVAE.forward of the UNMODIFIED reference at its native shape (the decoder's reshape is
+    hard-wired to it): x_recon, h_seq, z_seq and the decoder LSTM output, soft and hard."""
+    fh, fw = hw
+    for _ in range(3):
+        fh, fw = (fh - 1) // 2 + 1, (fw - 1) // 2 + 1
+    sd = rbvae.init_state_dict(cin, L, (fh, fw), channels=ch, num_layers=layers, seed=seed)
+    sd.update(rbvae.init_decoder_state_dict(cin, L, (fh, fw), channels=ch, num_layers=layers, seed=seed))
+    m = ref_shim.rbvae(kind, cin, L, sd)
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.randn(B, T, cin, *hw, generator=g) * 0.7 if kind == "percep" else torch.rand(B, T, cin, *hw, generator=g)
+    out = {}
+    with torch.no_grad():
+        for tag, hard, temp, nr, s0 in (("soft", False, 1.0, 0.1, 901), ("hard", True, 0.5, 0.0, 902)):
+            torch.manual_seed(s0)
+            x_recon, h_seq, z_seq = m(x, temperature=temp, hard=hard, noise_ratio=nr)
+            torch.manual_seed(s0)
+            U = torch.rand(B * T, L)          # the draw binary_concrete_logits made (percep_RBVAE_model.py:33)
+            d_seq, _ = m.decoder_rnn(z_seq)
+            out.update({f"x_recon_{tag}": x_recon.numpy(), f"h_{tag}": h_seq.numpy(), f"z_{tag}": z_seq.numpy(),
+                        f"d_{tag}": d_seq.numpy(), f"U_{tag}": U.numpy()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, cin=cin, ch=ch, layers=layers, L=L, hw=np.array(hw),
+                        seed=seed, B=B, T=T, x=x.numpy(), **out)
+    print(name, "x_recon range", float(out["x_recon_soft"].min()), float(out["x_recon_soft"].max()))
+
+
+def losses_case():
+    """The reference's own loss functions (percep_RBVAE_train.py:27-107, cut out unmodified) on seeded inputs."""
+    fn = ref_shim.train_loss_functions()
+    g = torch.Generator().manual_seed(4242)
+    N, L, D = 12, 25, 25
+    q = torch.randn(N, L, generator=g) * 3
+    q[0, :3] = torch.tensor([40.0, -40.0, 0.0])          # saturated sigmoid: the clamp / eps branches
+    a, p, n = (torch.randn(N, D, generator=g) for _ in range(3))
+    label = (torch.rand(N, generator=g) > 0.5).float()
+    xr, x = torch.rand(2, 3, 4, 8, 16, generator=g), torch.rand(2, 3, 4, 8, 16, generator=g)
+    res = dict(l1=fn["l1_loss"](q, 0.01), mse=fn["recon_loss"](xr, x),
+               triplet_swap=fn["triplet_loss"](a, p, n), triplet_noswap=fn["triplet_loss"](a, p, n, margin=0.5, swap=False),
+               kl_half=fn["kl_binary_concrete"](q), kl_p03=fn["kl_binary_concrete"](q, p=0.3),
+               contrast_euclid=fn["contrast_loss"](a, p, label), contrast_cos=fn["contrast_loss"](a, p, label, margin=0.7, dist="cosine"))
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), q=q.numpy(), a=a.numpy(), p=p.numpy(), n=n.numpy(), label=label.numpy(),
+                        xr=xr.numpy(), x=x.numpy(), **{k: np.float32(v.item()) for k, v in res.items()})
+    print("losses", {k: float(v) for k, v in res.items()})
+
+
 def resize_case():
     """PIL LANCZOS on the first chinchess frame (768x432 -> 1280x720 -> 1280x704), subsampled."""
     import cv2
@@ -276,6 +321,10 @@ def main():
         return evaluation_case()
     if "--only-dataset" in sys.argv:
         return dataset_case()
+    if "--only-forward" in sys.argv:
+        rbvae_forward_case("rbvae_forward_percep_L25_88x160", "percep", 4, 256, 4, 25, (88, 160), 11, 1, 2)
+        rbvae_forward_case("rbvae_forward_contrastive_L25_256x256", "contrastive", 3, 64, 2, 25, (256, 256), 12, 1, 1)
+        return losses_case()
     encoder_case("kl_f8_seed0_2x64x96_white", 0, (2, 64, 96), 1234, False)
     encoder_case("kl_f8_seed1_1x128x128_smooth", 1, (1, 128, 128), 1234, True)
     encoder_case("kl_f8_seed0_2x256x256_white", 0, (2, 256, 256), 1234, False)      # BASELINE config 1 shape
@@ -284,6 +333,9 @@ def main():
     rbvae_case("rbvae_percep_L100_88x160_T1", "percep", 4, 256, 4, 100, (88, 160), 3, 1)   # reference-native shape
     rbvae_case("rbvae_percep_L50_32x32_T4", "percep", 4, 256, 4, 50, (32, 32), 4, 4)
     rbvae_case("rbvae_contrastive_L25_256x256_T1", "contrastive", 3, 64, 2, 25, (256, 256), 5, 1)
+    rbvae_forward_case("rbvae_forward_percep_L25_88x160", "percep", 4, 256, 4, 25, (88, 160), 11, 1, 2)
+    rbvae_forward_case("rbvae_forward_contrastive_L25_256x256", "contrastive", 3, 64, 2, 25, (256, 256), 12, 1, 1)
+    losses_case()
     resize_case()
     chinchess_case()
     evaluation_case()

@@ -1,4 +1,5 @@
-"""Oracle: functional fp32 restatement of the RBVAE *encoder* path.
+"""Oracle: functional fp32 restatement of the RBVAE encoder path and (training-side forward) of its
+decoder half.
 
 TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Citations are ``path:line``
 under /root/reference/.  Two families share one code path:
@@ -90,6 +91,60 @@ def encode(x, sd, temperature=0.5, hard=False, noise_ratio=0.1, U=None, return_h
                             None if U is None else U.reshape(B * T, L))
         z_seq = z.reshape(B, T, L)
     return (z_seq, h_seq) if return_h else z_seq
+
+
+def decode(z_seq, sd, feat_hw):
+    """Second half of Seq2SeqBinaryVAE.forward, percep_RBVAE_model.py:159-168:
+    d_seq = decoder_rnn(z_seq); x_recon = decoder_cnn(d_seq) = sigmoid(deconv3(relu(deconv2(relu(deconv1(fc(d)))))));
+    each deconv is ConvTranspose2d(3, stride 2, padding 1, output_padding 1) (:75-84), dropout = identity (eval).
+    z_seq: [B,T,L] -> (x_recon [B,T,C,H,W], d_seq [B,T,L])."""
+    with torch.no_grad():
+        B, T, L = z_seq.shape
+        d_seq = lstm_forward(z_seq, sd, prefix="decoder_rnn.lstm.")
+        p = "decoder_cnn.deconv."
+        ch = sd[p + "0.weight"].shape[0]
+        h = F.linear(d_seq.reshape(B * T, L), sd["decoder_cnn.fc.weight"], sd["decoder_cnn.fc.bias"])
+        h = h.reshape(B * T, ch, feat_hw[0], feat_hw[1])      # the reference hard-wires (256, 11, 20) / (64, 32, 32)
+        h = F.relu(F.conv_transpose2d(h, sd[p + "0.weight"], sd[p + "0.bias"], stride=2, padding=1, output_padding=1))
+        h = F.relu(F.conv_transpose2d(h, sd[p + "3.weight"], sd[p + "3.bias"], stride=2, padding=1, output_padding=1))
+        h = torch.sigmoid(F.conv_transpose2d(h, sd[p + "6.weight"], sd[p + "6.bias"], stride=2, padding=1, output_padding=1))
+        x_recon = h.reshape(B, T, h.shape[1], h.shape[2], h.shape[3])
+    return x_recon, d_seq
+
+
+def forward(x, sd, temperature=1.0, hard=False, noise_ratio=0.1, U=None):
+    """Seq2SeqBinaryVAE.forward, percep_RBVAE_model.py:143-170 -> (x_recon, h_seq, z_seq)."""
+    z_seq, h_seq = encode(x, sd, temperature, hard, noise_ratio, U, return_h=True)
+    fh, fw = x.shape[-2], x.shape[-1]
+    for _ in range(3):
+        fh, fw = (fh - 1) // 2 + 1, (fw - 1) // 2 + 1
+    x_recon, _ = decode(z_seq, sd, (fh, fw))
+    return x_recon, h_seq, z_seq
+
+
+def init_decoder_state_dict(out_channels, latent_dim, feat_hw, channels=256, num_layers=4, seed=0):
+    """Seeded default-init decoder weights with the reference key names (ConvTranspose2d weights are [Cin,Cout,3,3])."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    sd = {}
+
+    def u(shape, bound):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+    fout = channels * feat_hw[0] * feat_hw[1]
+    b = 1.0 / latent_dim ** 0.5
+    sd["decoder_cnn.fc.weight"] = u((fout, latent_dim), b)
+    sd["decoder_cnn.fc.bias"] = u((fout,), b)
+    for idx, co in ((0, channels), (3, channels), (6, out_channels)):
+        b = 1.0 / (co * 9) ** 0.5
+        sd[f"decoder_cnn.deconv.{idx}.weight"] = u((channels, co, 3, 3), b)
+        sd[f"decoder_cnn.deconv.{idx}.bias"] = u((co,), b)
+    b = 1.0 / latent_dim ** 0.5
+    for l in range(num_layers):
+        sd[f"decoder_rnn.lstm.weight_ih_l{l}"] = u((4 * latent_dim, latent_dim), b)
+        sd[f"decoder_rnn.lstm.weight_hh_l{l}"] = u((4 * latent_dim, latent_dim), b)
+        sd[f"decoder_rnn.lstm.bias_ih_l{l}"] = u((4 * latent_dim,), b)
+        sd[f"decoder_rnn.lstm.bias_hh_l{l}"] = u((4 * latent_dim,), b)
+    return sd
 
 
 def pack_codes(z):

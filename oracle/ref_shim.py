@@ -144,3 +144,23 @@ def train_dataset_class():
         if isinstance(node, ast.ClassDef) and node.name == "ShuffledStatePairDataset":
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns["ShuffledStatePairDataset"]
+
+
+def train_loss_functions():
+    """The reference's loss functions, UNMODIFIED, executed from their own source text:
+    models/percep_RBVAE/percep_RBVAE_train.py imports wandb / torchvision datasets at module level, so the five
+    function definitions (:27-107) are cut out with ``ast`` and exec'd with the globals they use (torch, F, np).
+    Live tree only."""
+    import ast
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    path = os.path.join(LIVE_ROOT, "models/percep_RBVAE/percep_RBVAE_train.py")
+    src = open(path).read()
+    want = {"l1_loss", "recon_loss", "triplet_loss", "kl_binary_concrete", "contrast_loss"}
+    ns = {"torch": torch, "F": F, "np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    assert want <= set(ns), sorted(want - set(ns))
+    return ns

@@ -22,11 +22,12 @@ from .pipeline import (EncodeResult, FramePipeline, all_gather_ragged, all_gathe
                        shard_range)
 from .embedding_store import (FlatEmbeddingStore, ShuffledStatePairDataset, frame_key, load_embeddings_npy,
                               lookup_embedding, save_embeddings_npy)
-from . import evaluation, feeder, ops, precompute
+from . import evaluation, feeder, losses, ops, precompute
 from .feeder import ArraySource, Feeder, FrameDirSource, VideoSource
 from .precompute import PrecomputeResult, precompute_embeddings
 from .evaluation import (add_gaussian_noise, add_occlusion, assign_label, calculate_state_consistency,
                          labels_from_flags, perturb_frames, state_consistency)
-from .weights import init_encoder_state_dict, init_rbvae_state_dict, make_rbvae_responsive, synthetic_frames
+from .weights import (init_encoder_state_dict, init_rbvae_decoder_state_dict, init_rbvae_state_dict,
+                      make_rbvae_responsive, synthetic_frames)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

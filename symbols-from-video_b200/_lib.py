@@ -73,6 +73,16 @@ SIGNATURES = {
     "sfv_rbvae_encode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, _P, C.c_float, C.c_float, C.c_int32,
                                    _P, _P, _P, _P, C.c_size_t, _P]),
     "sfv_hamming": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P]),
+    "sfv_rbvae_decoder_create": (C.c_int, [C.POINTER(SfvTensor), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(_P)]),
+    "sfv_rbvae_decoder_destroy": (None, [_P]),
+    "sfv_rbvae_decoder_workspace_bytes": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_size_t)]),
+    "sfv_rbvae_decode": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "sfv_loss_mse": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "sfv_loss_l1": (C.c_int, [_P, C.c_int64, C.c_float, _P, _P]),
+    "sfv_loss_kl_binary_concrete": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_float, C.c_float, _P, _P]),
+    "sfv_loss_contrast": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),
+    "sfv_loss_triplet": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, _P, _P]),
     "sfv_state_consistency": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
     "sfv_perturb_frames": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_float, C.c_float,
                                      _P, C.c_int32, _P]),

@@ -230,6 +230,64 @@ int sfv_rbvae_workspace_bytes(const SfvRbvae* r, int32_t N, size_t* bytes) {
   *bytes = rbvae_workspace(r, N);
   return 0;
 }
+int sfv_rbvae_decoder_create(const SfvTensor* tensors, int32_t n_tensors, int32_t out_channels, int32_t out_h,
+                             int32_t out_w, SfvRbvaeDecoder** out) {
+  if (!out || !tensors) return fail(SFV_ERR_INVALID, "rbvae_decoder_create: null argument");
+  *out = nullptr;
+  if (out_channels < 1 || out_h < 8 || out_w < 8) return fail(SFV_ERR_INVALID, "rbvae_decoder_create: bad output shape");
+  SFV_TRY(require_device());
+  SfvRbvaeDecoder* r = new (std::nothrow) SfvRbvaeDecoder();
+  if (!r) return fail(SFV_ERR_INVALID, "out of host memory");
+  r->out_channels = out_channels; r->out_h = out_h; r->out_w = out_w;
+  if (cudaGetDevice(&r->device) != cudaSuccess) { delete r; return fail(SFV_ERR_CUDA, "cudaGetDevice failed"); }
+  int st = rbvae_decoder_build(r, tensors, n_tensors);
+  if (st != 0) { r->blob.release(); delete r; return st; }
+  *out = r;
+  return 0;
+}
+void sfv_rbvae_decoder_destroy(SfvRbvaeDecoder* r) {
+  if (!r) return;
+  r->blob.release();
+  delete r;
+}
+int sfv_rbvae_decoder_workspace_bytes(const SfvRbvaeDecoder* r, int32_t N, size_t* bytes) {
+  if (!r || !bytes || N < 1) return fail(SFV_ERR_INVALID, "rbvae_decoder_workspace_bytes: bad argument");
+  *bytes = rbvae_decoder_workspace(r, N);
+  return 0;
+}
+int sfv_rbvae_decode(SfvRbvaeDecoder* r, const float* z_seq, int32_t B, int32_t T, float* d_seq_out, float* x_recon,
+                     void* ws, size_t ws_bytes, void* stream) {
+  if (!r || !z_seq || !x_recon) return fail(SFV_ERR_INVALID, "rbvae_decode: null argument");
+  {
+    int dev = -1;
+    SFV_CUDA(cudaGetDevice(&dev));
+    SFV_CHECK(dev == r->device, "rbvae decoder: handle was created on device %d but device %d is current", r->device, dev);
+  }
+  return rbvae_decode(r, z_seq, B, T, d_seq_out, x_recon, ws, ws_bytes, (cudaStream_t)stream);
+}
+int sfv_loss_mse(const float* a, const float* b, int64_t n, float* out, void* stream) {
+  SFV_TRY(require_device());
+  return launch_mse(a, b, n, out, (cudaStream_t)stream);
+}
+int sfv_loss_l1(const float* q, int64_t n, float lamb, float* out, void* stream) {
+  SFV_TRY(require_device());
+  return launch_l1(q, n, lamb, out, (cudaStream_t)stream);
+}
+int sfv_loss_kl_binary_concrete(const float* q_logits, int64_t rows, int32_t L, float p, float eps, float* out, void* stream) {
+  SFV_TRY(require_device());
+  return launch_kl_binary_concrete(q_logits, rows, L, p, eps, out, (cudaStream_t)stream);
+}
+int sfv_loss_contrast(const float* x1, const float* x2, const float* label, int32_t rows, int32_t D, float margin,
+                      int32_t cosine, float* out, void* stream) {
+  SFV_TRY(require_device());
+  return launch_contrast(x1, x2, label, rows, D, margin, cosine, out, (cudaStream_t)stream);
+}
+int sfv_loss_triplet(const float* anchor, const float* pos, const float* neg, int32_t rows, int32_t D, float margin,
+                     float eps, int32_t swap, float* out, void* stream) {
+  SFV_TRY(require_device());
+  return launch_triplet(anchor, pos, neg, rows, D, margin, eps, swap, out, (cudaStream_t)stream);
+}
+
 int sfv_rbvae_encode(SfvRbvae* r, const float* x, int32_t B, int32_t T, float in_scale, const float* u,
                      float noise_ratio, float temperature, int32_t hard, float* h_out, float* z_out,
                      uint32_t* codes, void* ws, size_t ws_bytes, void* stream) {

@@ -96,7 +96,30 @@ struct SfvRbvae {
   float *w_ih = nullptr, *w_hh = nullptr, *lstm_b = nullptr;   // [layers][4L][L], [layers][4L]
 };
 
+// decoder half (training-side forward): decoder_rnn + ConvDecoder, fp32 on CUDA cores
+struct SfvRbvaeDecoder {
+  int device = -1;
+  int out_channels = 0, out_h = 0, out_w = 0, channels = 0, layers = 0, L = 0;
+  int fh = 0, fw = 0;                 // feature map the fc layer produces (out / 8)
+  sfv::DeviceBlob blob;
+  sfv::ConvW dc[3];                   // the three ConvTranspose2d as direct 3x3 convolutions over zero-stuffed inputs
+  float* fc_w = nullptr;              // [channels*fh*fw][L] (reference layout)
+  float* fc_b = nullptr;
+  float *w_ih = nullptr, *w_hh = nullptr, *lstm_b = nullptr;   // decoder_rnn: [layers][4L][L], [layers][4L]
+};
+
 namespace sfv {
+int rbvae_decoder_build(SfvRbvaeDecoder* r, const SfvTensor* t, int n);
+size_t rbvae_decoder_workspace(const SfvRbvaeDecoder* r, int N);
+int rbvae_decode(SfvRbvaeDecoder* r, const float* z_seq, int B, int T, float* d_seq, float* x_recon, void* ws, size_t ws_bytes,
+                 cudaStream_t s);
+int launch_mse(const float* a, const float* b, long long n, float* out, cudaStream_t s);
+int launch_l1(const float* q, long long n, float lamb, float* out, cudaStream_t s);
+int launch_kl_binary_concrete(const float* q_logits, long long rows, int L, float p, float eps, float* out, cudaStream_t s);
+int launch_contrast(const float* x1, const float* x2, const float* label, int rows, int D, float margin, int cosine, float* out,
+                    cudaStream_t s);
+int launch_triplet(const float* a, const float* p, const float* n, int rows, int D, float margin, float eps, int swap, float* out,
+                   cudaStream_t s);
 int encoder_build(SfvEncoder* e, const SfvTensor* t, int n);
 size_t encoder_workspace(const SfvEncoder* e, int B, int H, int W);
 int encoder_forward(SfvEncoder* e, const void* x, int src_kind, int B, int H, int W, float* params,

@@ -1,4 +1,5 @@
-"""Drop-in host mirror of the reference's RBVAE *encoder half*.
+"""Drop-in host mirror of the reference's RBVAE: the encoder half (the precompute hot path) and, when the state-dict
+carries it, the decoder half of ``forward`` (training-side forward; fp32, forward values only).
 
 * percep      -- models/percep_RBVAE/percep_RBVAE_model.py:125-191
                  (256-channel convs, 4-layer LSTM, fc hard-wired to 256*11*20)
@@ -10,7 +11,8 @@ the reference constructor; ``kind`` / ``input_hw`` are the extra knobs that let
 the fc layer follow the latent shape (the reference fails on anything but its
 native 88x160 / 256x256 input).  State-dict key names are the
 reference's, so ``load_state_dict(torch.load(...)['model_state_dict'])`` works
-unchanged (decoder keys are accepted and ignored).
+unchanged.  The decoder modules (``decoder_rnn``, ``decoder_cnn``) are created by ``load_state_dict`` when the
+state-dict has their keys; without them ``forward`` returns ``x_recon = None``.
 """
 from __future__ import annotations
 
@@ -55,6 +57,22 @@ class _Lstm(nn.Module):
                 self.lstm.register_parameter(f"{n}_l{l}", nn.Parameter(torch.zeros(shape), requires_grad=False))
 
 
+class _DeconvStack(nn.Module):
+    """ConvDecoder's parameters (percep_RBVAE_model.py:71-85): fc(L -> ch*fh*fw), three ConvTranspose2d."""
+
+    def __init__(self, cout, ch, latent_dim, fout):
+        super().__init__()
+        self.fc = nn.Module()
+        self.fc.weight = nn.Parameter(torch.zeros(fout, latent_dim), requires_grad=False)
+        self.fc.bias = nn.Parameter(torch.zeros(fout), requires_grad=False)
+        self.deconv = nn.Module()
+        for idx, co in ((0, ch), (3, ch), (6, cout)):     # Sequential indices of the three ConvTranspose2d
+            leaf = nn.Module()
+            leaf.weight = nn.Parameter(torch.zeros(ch, co, 3, 3), requires_grad=False)   # [Cin, Cout, 3, 3]
+            leaf.bias = nn.Parameter(torch.zeros(co), requires_grad=False)
+            self.deconv.add_module(str(idx), leaf)
+
+
 class Seq2SeqBinaryVAE(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, latent_dim=32, hidden_dim=32, kind=None, input_hw=None,
                  precision="fp32"):
@@ -78,11 +96,23 @@ class Seq2SeqBinaryVAE(nn.Module):
         fin = self.channels * _down3(self.input_hw[0]) * _down3(self.input_hw[1])
         self.encoder_cnn = _ConvStack(in_channels, self.channels, latent_dim, fin)
         self.encoder_rnn = _Lstm(latent_dim, cfg["layers"])
+        self.out_channels = out_channels
+        self.decoder_cnn = None         # created by load_state_dict when the checkpoint carries the decoder
+        self.decoder_rnn = None
+        self._dec_handles = {}
+        self._dec_ws = _lib.Workspace()
         self._handles = {}
         self._ws = _lib.Workspace()
 
     # -- weights -------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
+        if "decoder_cnn.fc.weight" in state_dict and "decoder_rnn.lstm.weight_ih_l0" in state_dict:
+            fout = state_dict["decoder_cnn.fc.weight"].shape[0]
+            layers = 0
+            while f"decoder_rnn.lstm.weight_ih_l{layers}" in state_dict:
+                layers += 1
+            self.decoder_cnn = _DeconvStack(self.out_channels, self.channels, self.latent_dim, fout)
+            self.decoder_rnn = _Lstm(self.latent_dim, layers)
         own = set(self.state_dict().keys())
         sd = {k: v for k, v in state_dict.items() if k in own}
         missing = own - set(sd)
@@ -101,6 +131,9 @@ class Seq2SeqBinaryVAE(nn.Module):
         for h in self._handles.values():
             _lib.lib().sfv_rbvae_destroy(h)
         self._handles = {}
+        for h in self._dec_handles.values():
+            _lib.lib().sfv_rbvae_decoder_destroy(h)
+        self._dec_handles = {}
 
     def __del__(self):
         try:
@@ -181,11 +214,53 @@ class Seq2SeqBinaryVAE(nn.Module):
                                        out_codes=out_codes, out_h=out_h)
         return codes, h_seq
 
+    # -- decoder half (training-side forward) ---------------------------------
+    def _native_decoder(self, H, W, device):
+        key = (H, W, torch.device(device))
+        if key not in self._dec_handles:
+            if H % 8 or W % 8:
+                raise ValueError(f"decoder output {H}x{W} must be a multiple of 8")
+            fout = self.channels * (H // 8) * (W // 8)
+            have = self.decoder_cnn.fc.weight.shape[0]
+            if fout != have:
+                # the reference reshapes fc's output to (ch, 11, 20) / (64, 32, 32) and fails likewise on other sizes
+                raise RuntimeError(f"shape '[-1, {self.channels}, {H // 8}, {W // 8}]' is invalid for fc.out_features {have}")
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith("decoder_")}
+            table, n, keep = _lib.make_tensor_table(sd)
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().sfv_rbvae_decoder_create(table, n, self.out_channels, H, W, C.byref(h)))
+            self._dec_handles[key] = h
+        return self._dec_handles[key]
+
+    @torch.no_grad()
+    def decode(self, z_seq, hw, return_d=False):
+        """decoder_rnn + decoder_cnn (percep_RBVAE_model.py:159-168): z_seq [B,T,L] -> x_recon [B,T,C,H,W], hw = (H, W)."""
+        if self.decoder_cnn is None:
+            raise RuntimeError("this model was loaded without decoder weights (decoder_cnn.* / decoder_rnn.*)")
+        _lib.require_cuda(z_seq, "z_seq")
+        B, T, L = z_seq.shape
+        if L != self.latent_dim:
+            raise ValueError(f"expected latent_dim {self.latent_dim}, got {L}")
+        H, W = hw
+        dev = z_seq.device
+        h = self._native_decoder(H, W, dev)
+        z = z_seq.to(torch.float32).contiguous()
+        d_seq = torch.empty(B, T, L, dtype=torch.float32, device=dev)
+        x_recon = torch.empty(B, T, self.out_channels, H, W, dtype=torch.float32, device=dev)
+        nbytes = C.c_size_t()
+        lib = _lib.lib()
+        _lib.check(lib.sfv_rbvae_decoder_workspace_bytes(h, B * T, C.byref(nbytes)))
+        ws = self._dec_ws.get(nbytes.value, dev)
+        _lib.run(lib.sfv_rbvae_decode, z, h, _lib.ptr(z), B, T, _lib.ptr(d_seq), _lib.ptr(x_recon), _lib.ptr(ws), nbytes.value)
+        return (x_recon, d_seq) if return_d else x_recon
+
     def forward(self, x, temperature=1.0, hard=False, noise_ratio=0.1, U=None):
-        """percep_RBVAE_model.py:143-170, encoder half: returns (x_recon, h_seq, z_seq)
-        with x_recon = None -- decoder_rnn / ConvDecoder belong to training."""
+        """percep_RBVAE_model.py:143-170: returns (x_recon, h_seq, z_seq).  x_recon is None when the model was loaded
+        without decoder weights (the precompute path needs the encoder half only)."""
         z_seq, h_seq, _ = self._encode(x, temperature, hard, noise_ratio, U)
-        return None, h_seq, z_seq
+        x_recon = self.decode(z_seq, x.shape[-2:]) if self.decoder_cnn is not None else None
+        return x_recon, h_seq, z_seq
 
 
 def unpack_codes(codes: torch.Tensor, L: int) -> torch.Tensor:

@@ -80,6 +80,32 @@ def init_rbvae_state_dict(in_channels, latent_dim, feat_hw, channels=256, num_la
     return sd
 
 
+def init_rbvae_decoder_state_dict(out_channels, latent_dim, feat_hw, channels=256, num_layers=4, seed=0) -> dict:
+    """RBVAE decoder half (decoder_rnn + decoder_cnn, reference key names and layouts); ``fc`` sized for a
+    (feat_h, feat_w) feature map = output / 8."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    sd = {}
+
+    def u(shape, bound):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+    fout = channels * feat_hw[0] * feat_hw[1]
+    b = 1.0 / latent_dim ** 0.5
+    sd["decoder_cnn.fc.weight"] = u((fout, latent_dim), b)
+    sd["decoder_cnn.fc.bias"] = u((fout,), b)
+    for idx, co in ((0, channels), (3, channels), (6, out_channels)):
+        b = 1.0 / (co * 9) ** 0.5                      # ConvTranspose2d: fan_in is counted over weight.size(1) = Cout
+        sd[f"decoder_cnn.deconv.{idx}.weight"] = u((channels, co, 3, 3), b)
+        sd[f"decoder_cnn.deconv.{idx}.bias"] = u((co,), b)
+    b = 1.0 / latent_dim ** 0.5
+    for l in range(num_layers):
+        sd[f"decoder_rnn.lstm.weight_ih_l{l}"] = u((4 * latent_dim, latent_dim), b)
+        sd[f"decoder_rnn.lstm.weight_hh_l{l}"] = u((4 * latent_dim, latent_dim), b)
+        sd[f"decoder_rnn.lstm.bias_ih_l{l}"] = u((4 * latent_dim,), b)
+        sd[f"decoder_rnn.lstm.bias_hh_l{l}"] = u((4 * latent_dim,), b)
+    return sd
+
+
 def make_rbvae_responsive(sd: dict, fc_gain: float = 40.0, bias_gain: float = 0.02, ih_gain: float = 4.0) -> dict:
     """Default-init RBVAE weights give ONE constant code whatever the frame (the LSTM biases decide every sign;
     per-bit std of h across frames ~5e-6), so a code comparison on them proves nothing.  No trained checkpoint

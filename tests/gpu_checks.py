@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 import sfv_b200  # noqa: E402
-from oracle import chinchess, evaluation as oev, frames, kl_f8, numerics_model, rbvae as orb  # noqa: E402
+from oracle import chinchess, evaluation as oev, frames, kl_f8, losses as olosses, numerics_model, rbvae as orb  # noqa: E402
 
 DEV = "cuda"
 
@@ -914,4 +914,126 @@ def check_edge_cases():
     st = sfv_b200.lib().sfv_rbvae_encode(h, lat.data_ptr(), 1, 1, 1.0, None, 0.3, 0.5, 1, hb.data_ptr(), None, None,
                                          ws.data_ptr(), nb.value, None)
     assert st == -1 and b"uniform draws" in sfv_b200.lib().sfv_last_error()
+    return out
+
+
+# ---- decoder half + losses (training-side forward) ------------------------------------------------------
+def rb_full_from_golden(g):
+    """Product model with encoder AND decoder weights of a forward golden, plus the state-dict and feature size."""
+    hw = [int(v) for v in g["hw"]]
+    fh, fw = hw
+    for _ in range(3):
+        fh, fw = (fh - 1) // 2 + 1, (fw - 1) // 2 + 1
+    kw = dict(channels=int(g["ch"]), num_layers=int(g["layers"]), seed=int(g["seed"]))
+    sd = orb.init_state_dict(int(g["cin"]), int(g["L"]), (fh, fw), **kw)
+    sd.update(orb.init_decoder_state_dict(int(g["cin"]), int(g["L"]), (fh, fw), **kw))
+    m = sfv_b200.Seq2SeqBinaryVAE(int(g["cin"]), int(g["cin"]), int(g["L"]), int(g["L"]), kind=str(g["kind"]), input_hw=tuple(hw))
+    m.load_state_dict(sd)
+    return m, sd, (fh, fw)
+
+
+def check_decoder_golden(name):
+    """Seq2SeqBinaryVAE.forward (x_recon, h_seq, z_seq) and .decode through the C ABI against the UNMODIFIED reference's
+    outputs at its native shape (percep 88x160, contrastive 256x256), soft and hard."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    m, sd, feat = rb_full_from_golden(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    out = dict(case=name)
+    for tag, hard, temp, nr in (("soft", False, 1.0, 0.1), ("hard", True, 0.5, 0.0)):
+        xr, h, z = m.forward(x, temperature=temp, hard=hard, noise_ratio=nr, U=torch.from_numpy(g[f"U_{tag}"]))
+        assert xr.shape == x.shape
+        out[f"h_{tag}"] = float(np.abs(h.cpu().numpy() - g[f"h_{tag}"]).max())
+        assert out[f"h_{tag}"] < 2e-5, out
+        if hard:
+            o, i, nb = code_flips(z.cpu().numpy(), g["z_hard"], g["h_hard"])
+            assert o == 0, (out, o, i, nb)
+        else:
+            out["z_soft"] = float(np.abs(z.cpu().numpy() - g["z_soft"]).max())
+            assert out["z_soft"] < 2e-5, out
+        # decoder on the reference's own z_seq (independent of the encoder half's last-ulp differences)
+        xd, d = m.decode(torch.from_numpy(g[f"z_{tag}"]).to(DEV), x.shape[-2:], return_d=True)
+        out[f"d_{tag}"] = float(np.abs(d.cpu().numpy() - g[f"d_{tag}"]).max())
+        out[f"x_recon_{tag}"] = float(np.abs(xd.cpu().numpy() - g[f"x_recon_{tag}"]).max())
+        assert out[f"d_{tag}"] < 2e-6 and out[f"x_recon_{tag}"] < 2e-6, out
+        if not hard:     # end to end: the encoder half's h differs in the last bits, the soft z carries that through
+            out["x_recon_e2e"] = float(np.abs(xr.cpu().numpy() - g["x_recon_soft"]).max())
+            assert out["x_recon_e2e"] < 1e-5, out
+    # the variation the comparison sees is real, not a constant image
+    out["x_recon_std"] = float(g["x_recon_soft"].std())
+    assert out["x_recon_std"] > 1e-3
+    sfv_b200._lib.check_async_error(torch.device(DEV, torch.cuda.current_device()))
+    return out
+
+
+def check_decoder_shapes():
+    """Decoder at shapes the reference's hard-wired reshape cannot run, against the oracle: T > 1, several frames,
+    percep 64x64 / 32x96 and contrastive 64x64; plus the error behaviour."""
+    out = {}
+    for kind, cin, ch, layers, L, hw, B, T in (("percep", 4, 256, 4, 25, (64, 64), 2, 3), ("percep", 4, 256, 4, 7, (32, 96), 1, 5),
+                                                ("contrastive", 3, 64, 2, 40, (64, 64), 3, 2)):
+        feat = (hw[0] // 8, hw[1] // 8)
+        sd = orb.init_state_dict(cin, L, feat, channels=ch, num_layers=layers, seed=3)
+        sd.update(orb.init_decoder_state_dict(cin, L, feat, channels=ch, num_layers=layers, seed=3))
+        # livelier decoder than default init (whose output is 0.5 +- 0.03): scale the fc so the sigmoid sees a range
+        sd["decoder_cnn.fc.weight"] = sd["decoder_cnn.fc.weight"] * 8
+        m = sfv_b200.Seq2SeqBinaryVAE(cin, cin, L, L, kind=kind, input_hw=hw)
+        m.load_state_dict(sd)
+        z = torch.rand(B, T, L, generator=torch.Generator().manual_seed(1))
+        xr, d = m.decode(z.to(DEV), hw, return_d=True)
+        xo, do = orb.decode(z, sd, feat)
+        key = f"{kind}_{hw[0]}x{hw[1]}_T{T}"
+        out[key] = (float(np.abs(xr.cpu().numpy() - xo.numpy()).max()), float(xo.std()))
+        assert out[key][0] < 2e-6 and out[key][1] > 5e-3, out
+        assert float(np.abs(d.cpu().numpy() - do.numpy()).max()) < 2e-6
+        for bad in ((hw[0] + 8, hw[1]), (hw[0] + 4, hw[1])):
+            try:
+                m.decode(z.to(DEV), bad)
+                raise AssertionError("decode accepted a shape its fc layer does not fit")
+            except (RuntimeError, ValueError):
+                pass
+    # a model loaded without decoder weights keeps the old contract
+    m = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, kind="percep", input_hw=(32, 32))
+    m.load_state_dict(orb.init_state_dict(4, 25, (4, 4), seed=1))
+    xr, h, z = m.forward(torch.randn(1, 1, 4, 32, 32).to(DEV), hard=True, noise_ratio=0.0)
+    assert xr is None and h.shape == (1, 1, 25)
+    try:
+        m.decode(z, (32, 32))
+        raise AssertionError("decode without decoder weights must raise")
+    except RuntimeError:
+        pass
+    return out
+
+
+def check_losses():
+    """The five training losses through the C ABI against the reference's own values (golden) and the oracle."""
+    from sfv_b200 import losses as L
+    g = np.load(os.path.join(GOLDEN, "losses.npz"))
+    t = {k: torch.from_numpy(g[k]).to(DEV) for k in ("q", "a", "p", "n", "label", "xr", "x")}
+    got = dict(l1=L.l1_loss(t["q"], 0.01), mse=L.recon_loss(t["xr"], t["x"]),
+               triplet_swap=L.triplet_loss(t["a"], t["p"], t["n"]),
+               triplet_noswap=L.triplet_loss(t["a"], t["p"], t["n"], margin=0.5, swap=False),
+               kl_half=L.kl_binary_concrete(t["q"]), kl_p03=L.kl_binary_concrete(t["q"], p=0.3),
+               contrast_euclid=L.contrast_loss(t["a"], t["p"], t["label"]),
+               contrast_cos=L.contrast_loss(t["a"], t["p"], t["label"], margin=0.7, dist="cosine"))
+    out = {}
+    for k, v in got.items():
+        out[k] = (float(v), float(g[k]))
+        assert v.dim() == 0 and v.is_cuda
+        assert abs(out[k][0] - out[k][1]) <= 1e-5 * max(1.0, abs(out[k][1])), (k, out[k])
+    # larger / odd sizes against the oracle (a reduction longer than one pass of the block, one row, one column)
+    gen = torch.Generator().manual_seed(11)
+    for N, D in ((1, 1), (3, 257), (700, 33)):
+        q = torch.randn(N, D, generator=gen) * 4
+        a, p, n = (torch.randn(N, D, generator=gen) for _ in range(3))
+        a[0] = p[0]
+        lb = (torch.rand(N, generator=gen) > 0.5).float()
+        big = torch.rand(5, 3, 4, 88, 160, generator=gen)
+        big2 = torch.rand(5, 3, 4, 88, 160, generator=gen)
+        pairs = [(L.l1_loss(q.to(DEV), 0.3), olosses.l1_loss(q, 0.3)), (L.recon_loss(big.to(DEV), big2.to(DEV)), olosses.recon_loss(big, big2)),
+                 (L.triplet_loss(a.to(DEV), p.to(DEV), n.to(DEV), margin=2.0), olosses.triplet_loss(a, p, n, margin=2.0)),
+                 (L.kl_binary_concrete(q.to(DEV), p=0.2), olosses.kl_binary_concrete(q, p=0.2)),
+                 (L.contrast_loss(a.to(DEV), p.to(DEV), lb.to(DEV)), olosses.contrast_loss(a, p, lb)),
+                 (L.contrast_loss(a.to(DEV), p.to(DEV), lb.to(DEV), dist="cosine"), olosses.contrast_loss(a, p, lb, dist="cosine"))]
+        for i, (c, o) in enumerate(pairs):
+            assert abs(float(c) - float(o)) <= 2e-5 * max(1.0, abs(float(o))), (N, D, i, float(c), float(o))
     return out

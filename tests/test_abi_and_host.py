@@ -108,10 +108,22 @@ def test_rbvae_state_dict_keys_and_fc_resize():
     assert rb.encoder_cnn.fc.weight.shape == (25, 256 * 11 * 20)       # reference default, percep_RBVAE_model.py:61
     ref = orb.init_state_dict(4, 25, (11, 20), seed=0)
     assert set(ref) == set(rb.state_dict())
-    # a checkpoint also carries decoder keys (percep_RBVAE_train.py:697-702) -> ignored
-    ck = dict(ref); ck["decoder_cnn.fc.weight"] = torch.zeros(3); ck["decoder_rnn.lstm.weight_ih_l0"] = torch.zeros(3)
+    assert rb.decoder_cnn is None and rb.decoder_rnn is None            # encoder half only until a checkpoint brings the rest
+    # a checkpoint also carries the decoder (percep_RBVAE_train.py:697-702) -> the decoder modules appear, reference keys
+    ck = dict(ref); ck.update(orb.init_decoder_state_dict(4, 25, (11, 20), seed=0))
     rb.load_state_dict(ck)
     assert torch.equal(rb.state_dict()["encoder_rnn.lstm.bias_hh_l3"], ref["encoder_rnn.lstm.bias_hh_l3"])
+    assert set(rb.state_dict()) == set(ck)
+    assert rb.decoder_cnn.fc.weight.shape == (256 * 11 * 20, 25)        # percep_RBVAE_model.py:74
+    assert rb.decoder_cnn.deconv._modules["6"].weight.shape == (256, 4, 3, 3)     # ConvTranspose2d: [Cin, Cout, 3, 3]
+    assert torch.equal(rb.state_dict()["decoder_rnn.lstm.weight_hh_l2"], ck["decoder_rnn.lstm.weight_hh_l2"])
+    # the product's own seeded decoder init uses the same keys and shapes
+    own = sfv_b200.init_rbvae_decoder_state_dict(4, 25, (11, 20), seed=0)
+    assert {k: tuple(v.shape) for k, v in own.items()} == {k: tuple(v.shape) for k, v in ck.items() if k.startswith("decoder_")}
+    # a truncated decoder is a strict-mode error, as with nn.Module.load_state_dict
+    bad = dict(ref); bad["decoder_cnn.fc.weight"] = ck["decoder_cnn.fc.weight"]; bad["decoder_rnn.lstm.weight_ih_l0"] = ck["decoder_rnn.lstm.weight_ih_l0"]
+    with pytest.raises(RuntimeError):
+        sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25).load_state_dict(bad)
     # square BASELINE shapes: fc follows the latent shape
     rb2 = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25, input_hw=(64, 64))
     assert rb2.encoder_cnn.fc.weight.shape == (25, 256 * 8 * 8)

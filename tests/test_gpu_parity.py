@@ -175,3 +175,17 @@ def test_encode_host_posterior_sampling(prec):
 
 def test_fused_groupnorm_transform_matches_default_path():
     print(_c().check_gn_fused_transform())
+
+
+# ---- decoder half + losses: the training-side forward ----
+@pytest.mark.parametrize("name", ["rbvae_forward_percep_L25_88x160", "rbvae_forward_contrastive_L25_256x256"])
+def test_rbvae_forward_with_decoder_golden(name):
+    print(_c().check_decoder_golden(name))
+
+
+def test_rbvae_decoder_other_shapes_and_errors():
+    print(_c().check_decoder_shapes())
+
+
+def test_training_losses():
+    print(_c().check_losses())
