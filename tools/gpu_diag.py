@@ -72,7 +72,10 @@ def plan():
               ("precompute/mixed", "check_precompute_driver('mixed')"), ("precompute/fp32", "check_precompute_driver('fp32')"),
               ("dataset/device", "check_resident_dataset()"),
               ("gn_fused", "check_gn_fused_transform()"),
-              ("sampling/fp32", "check_encode_host_sampling('fp32')"), ("sampling/mixed", "check_encode_host_sampling('mixed')")]
+              ("sampling/fp32", "check_encode_host_sampling('fp32')"), ("sampling/mixed", "check_encode_host_sampling('mixed')"),
+              ("decoder/percep", "check_decoder_golden('rbvae_forward_percep_L25_88x160')"),
+              ("decoder/contrastive", "check_decoder_golden('rbvae_forward_contrastive_L25_256x256')"),
+              ("decoder/shapes", "check_decoder_shapes()"), ("losses", "check_losses()")]
     return items
 
 
