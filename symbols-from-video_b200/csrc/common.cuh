@@ -159,6 +159,10 @@ struct IgemmArgs {
   long long ldy;             // output row pitch (elements)
   int nchw_out;              // write y as NCHW [N,Cout,Ho,Wo] instead
   int* err16;                // with fmt16 == FMT_F16: flag a y16 store beyond the fp16 range here (range-checked modes)
+  int ksize_x;               // kernel width when it differs from ksize (= height); 0: square
+  // strided output (sub-pixel phases of a transposed convolution): pixel (oy, ox) of this launch is written at
+  // (oy * osy + ooy, ox * osx + oox) of an [oHf, oWf] image; osy == 0: dense [Ho, Wo] output
+  int osy, osx, ooy, oox, oHf, oWf;
 };
 int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s);
 // y16 != nullptr: write to16(y16_scale * value) there (format fmt16) instead of the fp32 y

@@ -9,9 +9,10 @@
 //   losses        l1_loss, recon_loss, triplet_loss, kl_binary_concrete, contrast_loss
 //                                                               percep_RBVAE_train.py:27-107
 //
-// ConvTranspose2d(k=3, s=2, p=1, output_padding=1) == a stride-1, pad-1 3x3 convolution with the flipped, transposed
-// kernel over the input with one zero inserted after every element (size 2H x 2W): the zero-stuffed tensor is written
-// by a small kernel and the existing fp32 implicit-GEMM convolution does the rest.
+// ConvTranspose2d(k=3, s=2, p=1, output_padding=1) by sub-pixel phases: output pixel (2y+a, 2x+b) only sees the taps
+// whose parity matches -- a = 0: ky = 1 on input row y; a = 1: ky = 2 on row y and ky = 0 on row y+1 (likewise in x).
+// Each of the four phases is a small dense convolution (1x1, 1x2, 2x1, 2x2 taps, 9 in total instead of the 36 a
+// zero-stuffed 3x3 convolution would execute) run by the fp32 implicit-GEMM kernel with a strided output.
 #include "common.cuh"
 #include "encoder.h"
 #include <string.h>
@@ -43,20 +44,6 @@ __global__ void fc_decode_kernel(const float* __restrict__ d, const float* __res
   out[i] = a + b[j];
 }
 
-// out[n][2y+a][2x+b][c] = (a == 0 && b == 0) ? in[n][y][x][c] : 0      (NHWC, C % 4 == 0)
-__global__ void zero_stuff_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C4);
-  long long p = i / C4;
-  const int xo = (int)(p % (2 * W)); p /= (2 * W);
-  const int yo = (int)(p % (2 * H));
-  const long long n = p / (2 * H);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (((xo | yo) & 1) == 0) v = in[((n * H + (yo >> 1)) * W + (xo >> 1)) * C4 + c];
-  out[i] = v;
-}
-
 // NHWC conv output -> sigmoid -> NCHW  (nn.Sigmoid at the end of ConvDecoder.deconv)
 __global__ void sigmoid_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, long long HW, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // NCHW index
@@ -69,7 +56,7 @@ __global__ void sigmoid_nchw_kernel(const float* __restrict__ in, float* __restr
   out[i] = 1.f / (1.f + expf(-v));
 }
 
-// ---- losses: one block, double accumulators, deterministic ------------------------------------------------------
+// ---- losses: double accumulators, fixed summation order (deterministic) --------------------------------------------
 __device__ double block_sum(double v) {
   __shared__ double sh[32];
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -84,33 +71,66 @@ __device__ double block_sum(double v) {
   return t;       // valid in thread 0
 }
 
+// The element-wise losses run as ONE cluster of eight CTAs: every CTA reduces its stride of the data, the partial sums
+// meet in CTA 0 through distributed shared memory in rank order (deterministic, no scratch buffer, no atomics).
+constexpr int kLossCtas = 8;
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// block_sum over the block, then over the cluster; the total is valid in thread 0 of CTA 0
+__device__ double cluster_sum(double v) {
+  __shared__ double part;
+  v = block_sum(v);
+  if (threadIdx.x == 0) part = v;
+  cluster_barrier();
+  double t = 0.0;
+  if (cluster_rank() == 0 && threadIdx.x == 0) {
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&part);
+    for (uint32_t r = 0; r < (uint32_t)kLossCtas; ++r) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      double pv;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(pv) : "r"(remote) : "memory");
+      t += pv;
+    }
+  }
+  cluster_barrier();            // nobody leaves while CTA 0 may still read its shared memory
+  return t;
+}
+
 // F.mse_loss(a, b): mean of squared differences
-__global__ void mse_kernel(const float* a, const float* b, long long n, float* out) {
+__global__ void __cluster_dims__(kLossCtas, 1, 1) mse_kernel(const float* a, const float* b, long long n, float* out) {
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float d = a[i] - b[i]; s += (double)(d * d); }
-  s = block_sum(s);
-  if (threadIdx.x == 0) *out = (float)(s / (double)n);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)kLossCtas * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += (double)(d * d);
+  }
+  s = cluster_sum(s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (float)(s / (double)n);
 }
 // lamb * torch.norm(q, p=1)
-__global__ void l1_kernel(const float* q, long long n, float lamb, float* out) {
+__global__ void __cluster_dims__(kLossCtas, 1, 1) l1_kernel(const float* q, long long n, float lamb, float* out) {
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)fabsf(q[i]);
-  s = block_sum(s);
-  if (threadIdx.x == 0) *out = lamb * (float)s;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)kLossCtas * blockDim.x)
+    s += (double)fabsf(q[i]);
+  s = cluster_sum(s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = lamb * (float)s;
 }
 // kl_binary_concrete (percep_RBVAE_train.py:52-77): q = clamp(sigmoid(logit), eps, 1 - eps);
 // kl = q (log(q + eps) - log p) + (1 - q)(log(1 - q + eps) - log(1 - p)); sum over the latent dim, mean over the rest
-__global__ void kl_kernel(const float* q_logits, long long rows, int L, float log_p, float log_1mp, float eps, float* out) {
+__global__ void __cluster_dims__(kLossCtas, 1, 1) kl_kernel(const float* q_logits, long long rows, int L, float log_p, float log_1mp,
+                                                             float eps, float* out) {
   double s = 0.0;
   const long long n = rows * L;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)kLossCtas * blockDim.x) {
     float q = 1.f / (1.f + expf(-q_logits[i]));
     q = fminf(fmaxf(q, eps), 1.0f - eps);
     const float kl = q * (logf(q + eps) - log_p) + (1.0f - q) * (logf((1.0f - q) + eps) - log_1mp);
     s += (double)kl;
   }
-  s = block_sum(s);
-  if (threadIdx.x == 0) *out = (float)(s / (double)rows);
+  s = cluster_sum(s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = (float)(s / (double)rows);
 }
 // F.pairwise_distance(x, y, p=2, eps): || x - y + eps ||_2 per row
 __device__ float row_dist(const float* x, const float* y, int D, float eps) {
@@ -175,7 +195,6 @@ int rbvae_decoder_build(SfvRbvaeDecoder* r, const SfvTensor* t, int n) {
     return fail(SFV_ERR_MISSING_KEY, "rbvae decoder: fc.out_features %lld does not match %d*%d*%d for a %dx%d output",
                 (long long)fcw->shape[0], r->channels, r->fh, r->fw, r->out_h, r->out_w);
   SFV_CHECK(r->L >= 1 && r->L <= 256, "rbvae decoder: latent_dim %d out of range [1,256]", r->L);
-  SFV_CHECK(r->channels % 4 == 0, "rbvae decoder: %d channels (must be a multiple of 4)", r->channels);
   SFV_TRY(r->blob.upload(fcw->host_data, (size_t)F * r->L * 4, (void**)&r->fc_w));
   SFV_TRY(r->blob.upload(fcb->host_data, (size_t)F * 4, (void**)&r->fc_b));
   const char* names[3] = {"decoder_cnn.deconv.0", "decoder_cnn.deconv.3", "decoder_cnn.deconv.6"};
@@ -185,17 +204,23 @@ int rbvae_decoder_build(SfvRbvaeDecoder* r, const SfvTensor* t, int n) {
     const int cin = r->channels, cout = i == 2 ? r->out_channels : r->channels;
     if (!ww || !bb || ww->shape[0] != cin || ww->shape[1] != cout || ww->shape[2] != 3 || ww->shape[3] != 3)
       return fail(SFV_ERR_MISSING_KEY, "rbvae decoder: missing/mis-shaped %s", names[i]);
-    // direct-convolution weight [co][ci][dy][dx] = transposed-convolution weight [ci][co][2-dy][2-dx]
-    const int cpad = cout;
-    std::vector<float> w((size_t)cpad * cin * 9, 0.f), b((size_t)cpad, 0.f);
-    for (int co = 0; co < cout; ++co) {
-      b[co] = bb->host_data[co];
-      for (int ci = 0; ci < cin; ++ci)
-        for (int dy = 0; dy < 3; ++dy)
-          for (int dx = 0; dx < 3; ++dx)
-            w[(((size_t)co * cin + ci) * 3 + dy) * 3 + dx] = ww->host_data[(((size_t)ci * cout + co) * 3 + (2 - dy)) * 3 + (2 - dx)];
-    }
-    SFV_TRY(make_conv_from_host(r->blob, w.data(), b.data(), cpad, cin, 3, 0, false, &r->dc[i]));
+    // phase (a, b), tap (r, s) of its (1+a) x (1+b) kernel reads input (y + r, x + s) with the transposed-convolution
+    // weight [ci][co][ky][kx], ky = a ? (r ? 0 : 2) : 1, kx likewise; igemm layout [(r*kw + s)*Cin + ci][Cout]
+    r->dc_cout[i] = cout;
+    SFV_TRY(r->blob.upload(bb->host_data, (size_t)cout * 4, (void**)&r->dc_bias[i]));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int kh = 1 + a, kw = 1 + b;
+        std::vector<float> w((size_t)kh * kw * cin * cout);
+        for (int rr = 0; rr < kh; ++rr)
+          for (int ss = 0; ss < kw; ++ss) {
+            const int ky = a ? (rr ? 0 : 2) : 1, kx = b ? (ss ? 0 : 2) : 1;
+            for (int ci = 0; ci < cin; ++ci)
+              for (int co = 0; co < cout; ++co)
+                w[((size_t)(rr * kw + ss) * cin + ci) * cout + co] = ww->host_data[(((size_t)ci * cout + co) * 3 + ky) * 3 + kx];
+          }
+        SFV_TRY(r->blob.upload(w.data(), w.size() * 4, (void**)&r->ph_w[i][a * 2 + b]));
+      }
   }
   int layers = 0;
   while (find_d(t, n, "decoder_rnn.lstm.weight_ih_l" + std::to_string(layers))) ++layers;
@@ -221,9 +246,17 @@ int rbvae_decoder_build(SfvRbvaeDecoder* r, const SfvTensor* t, int n) {
   return 0;
 }
 
-// frames that go through the transposed convolutions together (bounds the workspace: ~24 MB per 88x160 frame)
+// frames that go through the transposed convolutions together (bounds the workspace: ~4.5 MB per 88x160 frame)
+static size_t dec_bytes_a(const SfvRbvaeDecoder* r, int n) {      // fc output, second layer's output
+  return (size_t)n * (r->out_h / 2) * (r->out_w / 2) * r->channels * 4;
+}
+static size_t dec_bytes_b(const SfvRbvaeDecoder* r, int n) {      // first layer's output, last layer's output
+  const size_t l0 = (size_t)n * (r->out_h / 4) * (r->out_w / 4) * r->channels * 4;
+  const size_t l2 = (size_t)n * r->out_h * r->out_w * r->out_channels * 4;
+  return l0 > l2 ? l0 : l2;
+}
 static int dec_slice(const SfvRbvaeDecoder* r, int N) {
-  const long long per = (long long)r->out_h * r->out_w * r->channels * 4 * 2;     // the two largest tensors of a frame
+  const long long per = (long long)(dec_bytes_a(r, 1) + dec_bytes_b(r, 1));
   long long k = (1ll << 30) / (per > 0 ? per : 1);
   if (k < 1) k = 1;
   if (k > 4096) k = 4096;
@@ -234,9 +267,8 @@ size_t rbvae_decoder_workspace(const SfvRbvaeDecoder* r, int N) {
   const int ns = dec_slice(r, N);
   Arena ar(nullptr, 0);
   ar.take((size_t)N * r->L * 4);                                              // d_seq when the caller does not want it
-  const size_t big = (size_t)ns * r->out_h * r->out_w * r->channels * 4;      // zero-stuffed input of the last layer
-  ar.take(big);                                                               // ping
-  ar.take(big / 4 > (size_t)ns * r->out_h * r->out_w * 4 * 4 ? big / 4 : (size_t)ns * r->out_h * r->out_w * 4 * 4);   // pong
+  ar.take(dec_bytes_a(r, ns));
+  ar.take(dec_bytes_b(r, ns));
   return ar.off + 1024;
 }
 
@@ -249,9 +281,8 @@ int rbvae_decode(SfvRbvaeDecoder* r, const float* z_seq, int B, int T, float* d_
   const int ns = dec_slice(r, N);
   Arena ar(ws, ws_bytes);
   float* dbuf = (float*)ar.take((size_t)N * r->L * 4);
-  const size_t big = (size_t)ns * r->out_h * r->out_w * r->channels * 4;
-  float* ping = (float*)ar.take(big);
-  float* pong = (float*)ar.take(big / 4 > (size_t)ns * r->out_h * r->out_w * 4 * 4 ? big / 4 : (size_t)ns * r->out_h * r->out_w * 4 * 4);
+  float* bufA = (float*)ar.take(dec_bytes_a(r, ns));
+  float* bufB = (float*)ar.take(dec_bytes_b(r, ns));
   float* d = d_seq ? d_seq : dbuf;
   // decoder_rnn: the stacked LSTM over z_seq (no fc partials, no noise, no code)
   SFV_TRY(launch_lstm_code(z_seq, 0, nullptr, B, T, r->L, r->layers, r->w_ih, r->w_hh, r->lstm_b, nullptr, 0.f, 1.f, 0, d, nullptr,
@@ -260,23 +291,33 @@ int rbvae_decode(SfvRbvaeDecoder* r, const float* z_seq, int B, int T, float* d_
   for (int n0 = 0; n0 < N; n0 += ns) {
     const int nn = (N - n0) < ns ? (N - n0) : ns;
     int h = r->fh, w = r->fw;
-    {  // fc -> [nn][fh][fw][C] in pong
+    {  // fc -> [nn][fh][fw][C]
       const long long tot = (long long)nn * C * h * w;
-      fc_decode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d + (size_t)n0 * r->L, r->fc_w, r->fc_b, pong, nn, r->L, C, h * w);
+      fc_decode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d + (size_t)n0 * r->L, r->fc_w, r->fc_b, bufA, nn, r->L, C, h * w);
       SFV_LAUNCH_OK();
     }
+    float* cur = bufA;
+    float* nxt = bufB;
     for (int i = 0; i < 3; ++i) {
-      // pong [nn][h][w][C] -> zero-stuffed ping [nn][2h][2w][C] -> conv 3x3 s1 p1 (+ReLU) -> pong [nn][2h][2w][C or Cop]
-      const long long tot4 = (long long)nn * 2 * h * 2 * w * (C / 4);
-      zero_stuff_kernel<<<(unsigned)((tot4 + 255) / 256), 256, 0, s>>>((const float4*)pong, (float4*)ping, h, w, C / 4, tot4);
-      SFV_LAUNCH_OK();
+      // cur [nn][h][w][C] -> nxt [nn][2h][2w][Cout]: four sub-pixel phases, (+ReLU after the first two layers)
+      for (int ph = 0; ph < 4; ++ph) {
+        IgemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.x = cur; g.src_kind = SRC_NHWC_F32; g.w = r->ph_w[i][ph]; g.w_sk = r->dc_cout[i]; g.w_sn = 1;
+        g.bias = r->dc_bias[i]; g.y = nxt;
+        g.N = nn; g.H = h; g.W = w; g.Cin = C; g.Ho = h; g.Wo = w; g.Cout = r->dc_cout[i];
+        g.ksize = 1 + (ph >> 1); g.ksize_x = 1 + (ph & 1); g.stride = 1; g.pad = 0;
+        g.relu = i < 2 ? 1 : 0; g.alpha = 1.f; g.in_scale = 1.f; g.ldy = r->dc_cout[i];
+        g.osy = 2; g.osx = 2; g.ooy = ph >> 1; g.oox = ph & 1; g.oHf = 2 * h; g.oWf = 2 * w;
+        SFV_TRY(launch_igemm_f32(g, s));
+      }
       h *= 2; w *= 2;
-      SFV_TRY(conv_f32(r->dc[i], ping, SRC_NHWC_F32, nn, h, w, 1, 1, 1, nullptr, pong, i < 2 ? 1 : 0, 1.f, s));
+      float* t = cur; cur = nxt; nxt = t;
     }
-    // pong [nn][H][W][Co] -> sigmoid -> x_recon [nn][Co][H][W]
+    // cur [nn][H][W][Co] -> sigmoid -> x_recon [nn][Co][H][W]
     const long long HW = (long long)h * w;
     const long long tot = (long long)nn * Co * HW;
-    sigmoid_nchw_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(pong, x_recon + (size_t)n0 * Co * HW, Co, HW, tot);
+    sigmoid_nchw_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(cur, x_recon + (size_t)n0 * Co * HW, Co, HW, tot);
     SFV_LAUNCH_OK();
   }
   return 0;
@@ -285,20 +326,20 @@ int rbvae_decode(SfvRbvaeDecoder* r, const float* z_seq, int B, int T, float* d_
 // ---- losses --------------------------------------------------------------------------------------------------------
 int launch_mse(const float* a, const float* b, long long n, float* out, cudaStream_t s) {
   SFV_CHECK(a && b && out && n >= 1, "mse: bad arguments");
-  mse_kernel<<<1, 1024, 0, s>>>(a, b, n, out);
+  mse_kernel<<<kLossCtas, 1024, 0, s>>>(a, b, n, out);
   SFV_LAUNCH_OK();
   return 0;
 }
 int launch_l1(const float* q, long long n, float lamb, float* out, cudaStream_t s) {
   SFV_CHECK(q && out && n >= 1, "l1: bad arguments");
-  l1_kernel<<<1, 1024, 0, s>>>(q, n, lamb, out);
+  l1_kernel<<<kLossCtas, 1024, 0, s>>>(q, n, lamb, out);
   SFV_LAUNCH_OK();
   return 0;
 }
 int launch_kl_binary_concrete(const float* q_logits, long long rows, int L, float p, float eps, float* out, cudaStream_t s) {
   SFV_CHECK(q_logits && out && rows >= 1 && L >= 1 && p > 0.f && p < 1.f, "kl_binary_concrete: bad arguments");
   // the reference takes np.log of the python float p (float64) and lets torch round it to the tensor's float32
-  kl_kernel<<<1, 1024, 0, s>>>(q_logits, rows, L, (float)log((double)p), (float)log(1.0 - (double)p), eps, out);
+  kl_kernel<<<kLossCtas, 1024, 0, s>>>(q_logits, rows, L, (float)log((double)p), (float)log(1.0 - (double)p), eps, out);
   SFV_LAUNCH_OK();
   return 0;
 }

@@ -102,7 +102,9 @@ struct SfvRbvaeDecoder {
   int out_channels = 0, out_h = 0, out_w = 0, channels = 0, layers = 0, L = 0;
   int fh = 0, fw = 0;                 // feature map the fc layer produces (out / 8)
   sfv::DeviceBlob blob;
-  sfv::ConvW dc[3];                   // the three ConvTranspose2d as direct 3x3 convolutions over zero-stuffed inputs
+  float* ph_w[3][4] = {};             // the three ConvTranspose2d as four sub-pixel phase kernels each: [(1+a)(1+b)*Cin][Cout]
+  float* dc_bias[3] = {};
+  int dc_cout[3] = {};
   float* fc_w = nullptr;              // [channels*fh*fw][L] (reference layout)
   float* fc_b = nullptr;
   float *w_ih = nullptr, *w_hh = nullptr, *lstm_b = nullptr;   // decoder_rnn: [layers][4L][L], [layers][4L]

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const IgemmArgs a) {
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int M = a.Ho * a.Wo;
-  const int K = a.ksize * a.ksize * a.Cin;
+  const int ksx = a.ksize_x ? a.ksize_x : a.ksize;      // kernel width (height = ksize)
+  const int K = a.ksize * ksx * a.Cin;
   const float* Bp = a.w + (long long)img * a.w_batch;
 
   // A-gather assignment: thread -> (m = tid % 64, k = tid / 64 + 4 i)
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const IgemmArgs a) {
     if (vec) {
       const int tap = k0 / a.Cin;
       const int ci0 = k0 - tap * a.Cin;
-      const int r = tap / a.ksize, s = tap - r * a.ksize;
+      const int r = tap / ksx, s = tap - r * ksx;
       const int iy = voy * a.stride + r - a.pad, ix = vox * a.stride + s - a.pad;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (vm_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const IgemmArgs a) {
         if (m_ok && k < K) {
           const int tap = k / a.Cin;
           const int ci = k - tap * a.Cin;
-          const int r = tap / a.ksize, s = tap - r * a.ksize;
+          const int r = tap / ksx, s = tap - r * ksx;
           v = load_src(a, img, oy * a.stride + r - a.pad, ox * a.stride + s - a.pad, ci);
         }
         As[kk][am] = v;
@@ -128,8 +129,13 @@ __global__ void __launch_bounds__(256) igemm_f32_kernel(const IgemmArgs a) {
       if (n >= a.Cout) continue;
       float v = acc[i][j] * a.alpha;
       if (a.bias) v += a.bias[n];
-      const long long o = a.nchw_out ? (((long long)img * a.Cout + n) * M + mm)
-                                     : (((long long)img * M + mm) * a.ldy + n);
+      long long o;
+      if (a.osy) {
+        const int py = mm / a.Wo, px = mm - py * a.Wo;
+        o = (((long long)img * a.oHf + (py * a.osy + a.ooy)) * a.oWf + (px * a.osx + a.oox)) * a.ldy + n;
+      } else {
+        o = a.nchw_out ? (((long long)img * a.Cout + n) * M + mm) : (((long long)img * M + mm) * a.ldy + n);
+      }
       if (a.residual) v += a.residual[o];
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.y) a.y[o] = v;
@@ -148,7 +154,7 @@ int launch_igemm_f32(const IgemmArgs& a, cudaStream_t s) {
   const int M = a.Ho * a.Wo;
   dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN), a.N);
   SFV_CHECK(grid.y <= 65535, "igemm: Cout too large");
-  ProfScope prof(PROF_IGEMM, 2.0 * M * (double)a.N * a.Cout * a.ksize * a.ksize * a.Cin, s);
+  ProfScope prof(PROF_IGEMM, 2.0 * M * (double)a.N * a.Cout * a.ksize * (a.ksize_x ? a.ksize_x : a.ksize) * a.Cin, s);
   igemm_f32_kernel<<<grid, 256, 0, s>>>(a);
   SFV_LAUNCH_OK();
   return 0;
