@@ -210,6 +210,50 @@ constexpr int kBulkPieceBytes = 16384;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One ring piece of the 16-bit -> 16-bit apply pass with the format, the range check and the activation fixed at
+// compile time: under the power cap the SMs run at ~1.4 GHz and the general loop's ~100 instructions per 8 elements
+// (format / check / activation branches, 64-bit address arithmetic, two add-and-mask range checks) made this
+// HBM-bound pass partly issue-bound.  Here: ~50.  With SiLU the 1/2 of h = t/2 is folded into scale and shift
+// (exact: a power of two), so h is the FMA's result; range check = running |max| of the packed halves (NaN-propagating),
+// compared once at the end.  Bit-identical to the general loop.
+template <int FMT, bool CHK, bool SILU>
+__device__ __forceinline__ void gn_piece16(const uint8_t* __restrict__ buf, int C, int tc, int tr, int rows, int cntp,
+                                           const float (&sc)[8], const float (&sf)[8], uint4* __restrict__ yrow, long long ystep,
+                                           __half2& mxi, __half2& mxo) {
+  const uint8_t* src = buf + ((size_t)tr * C + tc * 8) * 2;
+  const size_t sstep = (size_t)rows * C * 2;
+#pragma unroll 2
+  for (int r = tr; r < cntp; r += rows, src += sstep, yrow += ystep) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    if (CHK) {
+      mxi = __hmax2_nan(__hmax2_nan(mxi, __habs2(*reinterpret_cast<const __half2*>(&u.x))), __habs2(*reinterpret_cast<const __half2*>(&u.y)));
+      mxi = __hmax2_nan(__hmax2_nan(mxi, __habs2(*reinterpret_cast<const __half2*>(&u.z))), __habs2(*reinterpret_cast<const __half2*>(&u.w)));
+    }
+    float v[8];
+    unpack2_16(u.x, FMT, v[0], v[1]); unpack2_16(u.y, FMT, v[2], v[3]);
+    unpack2_16(u.z, FMT, v[4], v[5]); unpack2_16(u.w, FMT, v[6], v[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = fmaf(v[j], sc[j], sf[j]);            // SILU: sc, sf already carry the 1/2
+      if (SILU) {
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+        v[j] = fmaf(h, th, h);
+      } else {
+        v[j] = h;
+      }
+    }
+    uint4 o;
+    o.x = pack2_16(v[0], v[1], FMT); o.y = pack2_16(v[2], v[3], FMT);
+    o.z = pack2_16(v[4], v[5], FMT); o.w = pack2_16(v[6], v[7], FMT);
+    if (CHK) {
+      mxo = __hmax2_nan(__hmax2_nan(mxo, __habs2(*reinterpret_cast<const __half2*>(&o.x))), __habs2(*reinterpret_cast<const __half2*>(&o.y)));
+      mxo = __hmax2_nan(__hmax2_nan(mxo, __habs2(*reinterpret_cast<const __half2*>(&o.z))), __habs2(*reinterpret_cast<const __half2*>(&o.w)));
+    }
+    *yrow = o;
+  }
+}
+
 template <bool IN16, bool OUT16>
 __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __restrict__ x, const double* __restrict__ stats,
                                                                const float* __restrict__ gamma,
@@ -269,6 +313,12 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
     sc[j] = gr * in_mul;                       // the stored input is (true value) / in_mul (scaled 16-bit stream)
     sf[j] = beta[c] - sh_mean[g] * gr;
   }
+  // lean 16-bit -> 16-bit path (see gn_piece16): tables with the SiLU's 1/2 folded in, packed-half running maxima
+  const bool lean = IN16 && OUT16;
+  float sch[8], sfh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sch[j] = do_silu ? 0.5f * sc[j] : sc[j]; sfh[j] = do_silu ? 0.5f * sf[j] : sf[j]; }
+  __half2 mxi = __float2half2_rn(0.f), mxo = __float2half2_rn(0.f);
   for (int piece = 0; piece < npieces; ++piece) {
     const int slot = piece % kBulkSlots;
     const uint32_t bar = smem_addr(&full[slot]);
@@ -287,6 +337,22 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
     const long long pp0 = (long long)piece * ppp;
     const int cntp = (int)min((long long)ppp, (p1 - p0) - pp0);
     const uint8_t* buf = ring + slot * kBulkPieceBytes;
+    if (lean) {
+      uint4* yrow = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + ((long long)n * HW + p0 + pp0 + tr) * C + tc * 8);
+      const long long ystep = (long long)rows * C / 8;
+      if (fmt == FMT_F16) {
+        if (chk) {
+          if (do_silu) gn_piece16<FMT_F16, true, true>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+          else gn_piece16<FMT_F16, true, false>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+        } else {
+          if (do_silu) gn_piece16<FMT_F16, false, true>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+          else gn_piece16<FMT_F16, false, false>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+        }
+      } else {
+        if (do_silu) gn_piece16<FMT_BF16, false, true>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+        else gn_piece16<FMT_BF16, false, false>(buf, C, tc, tr, rows, cntp, sch, sfh, yrow, ystep, mxi, mxo);
+      }
+    } else
     for (int r = tr; r < cntp; r += rows) {
       float v[8];
       if (IN16) {
@@ -323,6 +389,10 @@ __global__ void __launch_bounds__(256, 3) gn_apply_bulk_kernel(const void* __res
   if (chk) {
     if (sat_in & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_IN);
     if (sat_out & 0x80008000u) atomicCAS(err, 0, kErrRangeBase + SITE_GN_OUT);
+    if (lean) {      // |x| >= 65504 (what a saturating conversion leaves), inf or NaN in either half
+      if (!(__low2float(mxi) < 65504.f) || !(__high2float(mxi) < 65504.f)) atomicCAS(err, 0, kErrRangeBase + SITE_GN_IN);
+      if (!(__low2float(mxo) < 65504.f) || !(__high2float(mxo) < 65504.f)) atomicCAS(err, 0, kErrRangeBase + SITE_GN_OUT);
+    }
   }
 }
 
