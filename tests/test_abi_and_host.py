@@ -56,6 +56,25 @@ def test_no_cpu_fallback():
     rb = sfv_b200.Seq2SeqBinaryVAE(4, 4, 25, 25)
     with pytest.raises(sfv_b200.SfvError):
         rb.encode(torch.zeros(1, 1, 4, 88, 160))
+    # decoder half and losses: same rule -- no CPU path, loud errors
+    with pytest.raises(RuntimeError):
+        rb.decode(torch.zeros(1, 1, 25), (88, 160))                      # loaded without decoder weights
+    sd = orb.init_state_dict(4, 25, (11, 20), seed=0)
+    sd.update(orb.init_decoder_state_dict(4, 25, (11, 20), seed=0))
+    rb.load_state_dict(sd)
+    with pytest.raises(sfv_b200.SfvError):
+        rb.decode(torch.zeros(1, 1, 25), (88, 160))                      # CPU tensor -> refuse
+    from sfv_b200 import losses
+    a = torch.zeros(4, 8)
+    for call in (lambda: losses.l1_loss(a, 0.1), lambda: losses.recon_loss(a, a), lambda: losses.triplet_loss(a, a, a),
+                 lambda: losses.kl_binary_concrete(a), lambda: losses.contrast_loss(a, a, torch.zeros(4))):
+        with pytest.raises(sfv_b200.SfvError):
+            call()
+    with pytest.raises(NotImplementedError):
+        losses.triplet_loss(a, a, a, p=1.0)
+    h = C.c_void_p()
+    table, n, keep = sfv_b200._lib.make_tensor_table({k: v for k, v in sd.items() if k.startswith("decoder_")})
+    assert sfv_b200.lib().sfv_rbvae_decoder_create(table, n, 4, 88, 160, C.byref(h)) == -2
 
 
 def test_product_never_imports_oracle():
